@@ -1,0 +1,165 @@
+/*
+ * libmars5_b200.so — C ABI of the B200-native MARS5 hot path (AR decode -> multinomial-DDPM NAR -> Vocos iSTFT).
+ *
+ * The reference (Camb-ai/MARS5-TTS) is pure PyTorch and has no FFI; the three call sites this library replaces are
+ *   ar_generate(...)                inference.py:260-269   (def mars5/ar_generate.py:16-21)
+ *   perform_simple_inference(...)   inference.py:296-298   (def mars5/diffuser.py:399-400)
+ *   Mars5TTS.vocode(tokens)         inference.py:160-172   (3rd-party vocos.decode)
+ * Each entry point below names the reference function it stands in for.  Conventions: extern "C", int status
+ * returns (0 = ok), no exceptions, plain pointers and sizes, no torch types.  One context per GPU, not thread-safe.
+ * Data buffers are HOST or DEVICE pointers as selected by `mem` (M5_MEM_*); per-utterance length arrays are always
+ * HOST.  All work is enqueued on the context's own CUDA stream; calls return after the results are in the caller's
+ * buffers (host) or enqueued (device; use m5_sync).  Packed layouts: utterance b's rows follow utterance b-1's.
+ */
+#ifndef MARS5_B200_H
+#define MARS5_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M5_OK 0
+#define M5_ERR_ARG 1
+#define M5_ERR_CUDA 2
+#define M5_ERR_STATE 3
+#define M5_ERR_NOMEM 4
+#define M5_ERR_MISSING_WEIGHT 5
+
+#define M5_MEM_HOST 0
+#define M5_MEM_DEVICE 1
+
+#define M5_DT_F16 0
+#define M5_DT_F32 1
+
+typedef struct m5_ctx m5_ctx;
+
+/* Model hyper-parameters (reference: inference.py:105-110, mars5/model.py:44-67,165-242; Appendix C of SURVEY.md). */
+typedef struct {
+  /* AR CodecLM */
+  int32_t ar_dim, ar_heads, ar_layers, ar_hidden, ar_vocab, ar_text_vocab, ar_spk_layers, ar_spk_ff;
+  float ar_norm_eps;
+  /* NAR ResidualTransformer */
+  int32_t nar_dim, nar_heads, nar_enc_layers, nar_dec_layers, nar_spk_layers, nar_ff, nar_text_vocab;
+  int32_t n_classes; /* 1025 */
+  int32_t n_quant;   /* 8 */
+  float ln_eps;      /* 4e-5, model.py:13 */
+  float head_ln_eps; /* 1e-5, model.py:237 */
+  /* Vocos encodec-24khz head */
+  int32_t voc_feat, voc_dim, voc_inter, voc_layers, voc_nfft, voc_hop, voc_n_bw, voc_codebook;
+  /* limits used to size workspaces */
+  int32_t max_pos; /* rows of the sinusoidal tables */
+} m5_model_cfg;
+
+/* Named weight tensor living in DEVICE memory owned by the caller (kept alive for the context's lifetime). */
+typedef struct {
+  const char* name;
+  const void* ptr;
+  int64_t numel;
+  int32_t dtype; /* M5_DT_* */
+} m5_tensor;
+
+int m5_create(int device, const m5_model_cfg* cfg, const m5_tensor* tensors, int32_t n_tensors, m5_ctx** out);
+void m5_destroy(m5_ctx* ctx);
+const char* m5_last_error(m5_ctx* ctx);
+int m5_sync(m5_ctx* ctx);
+/* Number of kernels this library launched on ctx's stream since creation (bench.py's gpu_launches). */
+int64_t m5_launch_count(m5_ctx* ctx);
+int m5_num_sms(m5_ctx* ctx);
+
+/* ---- AR: replaces ar_generate (mars5/ar_generate.py:15-165) for B independent utterances ------------------- */
+typedef struct {
+  float temperature;     /* InferenceConfig.temperature */
+  int32_t top_k;         /* 0 disables */
+  float top_p;           /* 1.0 disables */
+  float alpha_frequency; /* freq_penalty */
+  float alpha_presence;  /* presence_penalty */
+  int32_t penalty_window;
+  float eos_penalty_decay, eos_penalty_factor;
+  int32_t max_len;      /* total length incl. prompt (ar_generate.py:62) */
+  int32_t eos_id;       /* len(texttok.vocab) + speechtok '<|endofspeech|>' (ar_generate.py:47) */
+  int32_t force_len;    /* benchmark only: >0 masks EOS until this many tokens were generated, then forces it */
+  int32_t sync_every;   /* host polls the all-done flag every this many steps (default 16) */
+} m5_ar_cfg;
+
+/*
+ * prompt_ids  [sum prompt_len]      text + (offset) speech-BPE ids, as built at inference.py:255
+ * spk_codes   [sum spk_len][8]      reference Encodec codes (spk_ref_codec, inference.py:242)
+ * n_phones_gen[B] (host)            round(factor*len(text)) for the EOS penalty (inference.py:268)
+ * noise       [B][noise_steps][V]   optional Exp(1) draws replacing torch.multinomial's (parity mode), else NULL
+ * out_ids     [B][max_len]          prompt followed by generated ids (EOS not appended, ar_generate.py:135)
+ * out_len, hit_maxlen [B] (host)
+ * logits_dump [B][dump_steps][V]    optional raw fp32 logits of the first dump_steps steps (same `mem` as data)
+ */
+int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int32_t* prompt_len,
+                   const int32_t* spk_codes, const int32_t* spk_len, const int32_t* n_phones_gen,
+                   const m5_ar_cfg* cfg, int32_t mem, const float* noise, int32_t noise_steps, uint64_t seed,
+                   const int64_t* utt_ids, int32_t* out_ids, int32_t* out_len, int32_t* hit_maxlen,
+                   float* logits_dump, int32_t dump_steps);
+
+/* ---- NAR: replaces perform_simple_inference (mars5/diffuser.py:398-472) ---------------------------------- */
+typedef struct {
+  int32_t T;          /* reverse steps (default_T = 200, inference.py:113) */
+  float x0_temp;      /* DSH.x_0_temp */
+  float guidance_w;   /* DSH.guidance_w */
+  int32_t q0_override_steps;
+  int32_t deep_clone;
+  int32_t precise;    /* 1: split-fp16 GEMM operands (fp32-class accuracy, 2x tensor work) */
+} m5_nar_cfg;
+
+/*
+ * c_text   [sum c_text_len]      text BPE ids
+ * c_codes  [sum c_codes_len][8]  reference codes (prompt)
+ * x_l0     [sum x_len]           AR L0 codes (the `_x[...,0]` column, inference.py:282)
+ * x_init   [sum x_len][8]        optional initial randint draw (diffuser.py:409) for parity, else NULL (Philox)
+ * noise    [T][2][sum S][8][K]   optional uniforms for the two rand_like draws per step (parity, tiny cases), else NULL
+ * out_codes[sum x_len][8]        result after the deep-clone crop (diffuser.py:471)
+ */
+int m5_nar_infer(m5_ctx* ctx, int32_t B, const int32_t* c_text, const int32_t* c_text_len, const int32_t* c_codes,
+                 const int32_t* c_codes_len, const int32_t* x_l0, const int32_t* x_len, const m5_nar_cfg* cfg,
+                 int32_t mem, const int32_t* x_init, const float* noise, uint64_t seed, const int64_t* utt_ids,
+                 int32_t* out_codes);
+
+/* One ResidualTransformer.forward (mars5/model.py:264-343): x [sum S][8] codes at timestep t -> logits
+ * [sum S][8][n_classes] fp32 (the reference's (bs,S,K,8) permuted as reverse_diffusion does, diffuser.py:359). */
+int m5_nar_forward(m5_ctx* ctx, int32_t B, const int32_t* c_text, const int32_t* c_text_len, const int32_t* c_codes,
+                   const int32_t* c_codes_len, const int32_t* x, const int32_t* x_len, int32_t t, int32_t drop_cond,
+                   int32_t precise, int32_t mem, float* logits_out);
+
+/* One CodecLM.forward over full prompts (mars5/model.py:95-141, no cache): logits [sum prompt_len][V] fp32. */
+int m5_ar_forward(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int32_t* prompt_len,
+                  const int32_t* spk_codes, const int32_t* spk_len, int32_t mem, float* logits_out);
+
+/* ---- Vocoder: replaces Mars5TTS.vocode (inference.py:160-172) -------------------------------------------- */
+/* codes [sum n_frames][8] -> wav [sum 320*n_frames] fp32 */
+int m5_vocode(m5_ctx* ctx, int32_t B, const int32_t* codes, const int32_t* n_frames, int32_t bandwidth_id,
+              int32_t mem, float* wav_out);
+
+/* ---- kernel-level entry points (device pointers) used by tests/ and bench.py's roofline leg -------------- */
+int m5_dbg_gemm(m5_ctx* ctx, const void* A_f16, const void* W_f16, int32_t M, int32_t N, int32_t K, int32_t kwrap,
+                const float* bias, const float* colscale, void* out, void* out_lo, int32_t ldc, int32_t mode,
+                int32_t act, int32_t accumulate, int32_t force_bn);
+int m5_dbg_skinny(m5_ctx* ctx, const void* X_f16, const void* W_f16, int32_t B, int32_t N, int32_t K, float* out_f32,
+                  void* out_f16, int32_t ldc, int32_t swiglu, int32_t accumulate);
+int m5_dbg_norm(m5_ctx* ctx, const float* x, int32_t M, int32_t D, const float* gamma, const float* beta, float eps,
+                int32_t rms, void* out_f16, void* out_lo_f16);
+int m5_dbg_attn(m5_ctx* ctx, const void* Q, const void* K, const void* V, int32_t ldq, int32_t ldk, int32_t ldv,
+                void* O, int32_t ldo, int32_t n_heads, int32_t n_seqs, int32_t max_q, const int32_t* q_start,
+                const int32_t* q_len, const int32_t* k_start, const int32_t* k_len, int32_t causal);
+int m5_dbg_decode_attn(m5_ctx* ctx, const void* q, const void* kc, const void* vc, int32_t B, int32_t H, int32_t W,
+                       const int32_t* kv_len, void* out, int32_t n_split);
+/* AR sampler chain on fp32 logits [B][V] (ar_generate.py:73-118): writes the chosen token per row. */
+int m5_dbg_sample(m5_ctx* ctx, const float* logits, int32_t B, int32_t V, const m5_ar_cfg* cfg, int32_t text_vocab,
+                  const int32_t* hist, int32_t hist_stride, const int32_t* n_gen, const int32_t* n_phones,
+                  const float* noise, uint64_t seed, int32_t* out_tok, float* out_logprobs);
+/* One reverse-diffusion posterior + sample (diffuser.py:359-393) from cond/uncond logits [R][8][K]. */
+int m5_dbg_posterior(m5_ctx* ctx, const float* cond, const float* uncond, int32_t R, int32_t t, int32_t T,
+                     float guidance_w, float x0_temp, const int32_t* x_t, const int32_t* x_known, const uint8_t* mask,
+                     const float* u_unknown, const float* u_known, uint64_t seed, int32_t* x_out);
+/* ISTFT head on [N][nfft+2] (mag-logits | phase) rows -> wav [hop*N] (Appendix C). */
+int m5_dbg_istft(m5_ctx* ctx, const float* spec, int32_t B, const int32_t* n_frames_dev_host, float* wav);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,299 @@
+// Attention kernels of the hot path (head_dim = 64 everywhere: nn_future.py:149, model.py nhead=16 x 64).
+//
+//  flash_attn_kernel : packed variable-length softmax(QK^T/8)V with online softmax; fp16 operands on the
+//                      mma.sync tensor path, fp32 softmax state.  Serves AR prefill (causal, nn_future.py:254-272),
+//                      the AR/NAR speaker encoders, the NAR encoder / decoder self-attention and the NAR
+//                      cross-attention (model.py:339-341 -> nn.MultiheadAttention).
+//  decode_attn_*     : single-query attention over the fp16 KV cache (AR decode step, nn_future.py:257-272),
+//                      split over the key axis so that B*H*n_split CTAs stream the cache at HBM rate.
+#include "m5_internal.h"
+#include "ptx.cuh"
+
+namespace m5 {
+
+static constexpr int FA_BQ = 64;   // queries per CTA (16 per warp)
+static constexpr int FA_BK = 64;   // keys per tile
+static constexpr int FA_THREADS = 128;
+static constexpr int HD = 64;
+
+// smem tile [rows][64] fp16, 16-byte chunks XOR-swizzled by (row & 7) -> conflict-free ldmatrix.
+__device__ __forceinline__ int sw_off(int row, int chunk) { return row * HD + ((chunk ^ (row & 7)) << 3); }
+
+__device__ __forceinline__ void load_tile_async(__half* dst, const __half* src, int ld, int rows_valid, int tid) {
+  // 64 rows x 8 chunks = 512 chunks, 4 per thread
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = tid + i * FA_THREADS;
+    const int row = c >> 3, chunk = c & 7;
+    const bool ok = row < rows_valid;
+    cp_async16(dst + sw_off(row, chunk), ok ? (src + (size_t)row * ld + chunk * 8) : src, ok);
+  }
+}
+
+__global__ void __launch_bounds__(FA_THREADS)
+flash_attn_kernel(AttnCall p) {
+  const int seq = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
+  const int q_len = p.q_len[seq], k_len = p.k_len[seq];
+  const int q0 = qt * FA_BQ;
+  if (q0 >= q_len) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  __shared__ __align__(128) __half sQ[FA_BQ * HD];
+  __shared__ __align__(128) __half sK[2][FA_BK * HD];
+  __shared__ __align__(128) __half sV[2][FA_BK * HD];
+
+  const __half* Qg = p.Q + (size_t)(p.q_start[seq] + q0) * p.ldq + head * HD;
+  const __half* Kg = p.K + (size_t)p.k_start[seq] * p.ldk + head * HD;
+  const __half* Vg = p.V + (size_t)p.k_start[seq] * p.ldv + head * HD;
+  const int q_valid = min(FA_BQ, q_len - q0);
+  const int causal_off = k_len - q_len;
+  int k_end = k_len;  // keys this CTA must visit
+  if (p.causal) k_end = min(k_len, q0 + q_valid + causal_off);
+  const int n_tiles = (k_end + FA_BK - 1) / FA_BK;
+
+  load_tile_async(sQ, Qg, p.ldq, q_valid, tid);
+  if (n_tiles > 0) {
+    load_tile_async(sK[0], Kg, p.ldk, min(FA_BK, k_end), tid);
+    load_tile_async(sV[0], Vg, p.ldv, min(FA_BK, k_end), tid);
+  }
+  cp_async_commit();
+
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+  float m_i[2] = {-INFINITY, -INFINITY}, l_i[2] = {0.f, 0.f};
+  const float sl2 = p.scale * 1.4426950408889634f;
+  uint32_t qf[4][4];
+
+  for (int kt = 0; kt < n_tiles; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < n_tiles) {
+      const int kn = (kt + 1) * FA_BK;
+      load_tile_async(sK[buf ^ 1], Kg + (size_t)kn * p.ldk, p.ldk, min(FA_BK, k_end - kn), tid);
+      load_tile_async(sV[buf ^ 1], Vg + (size_t)kn * p.ldv, p.ldv, min(FA_BK, k_end - kn), tid);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (kt == 0) {
+      // Q fragments: rows warp*16 .. +15, 4 k-steps of 16
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int row = warp * 16 + (lane & 15);
+        const int chunk = kk * 2 + (lane >> 4);
+        ldmatrix_x4(qf[kk], sQ + sw_off(row, chunk));
+      }
+    }
+    // ---- S = Q K^T (16 x 64 per warp)
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-key n-tiles
+        uint32_t b[4];
+        const int row = jp * 16 + (lane & 7) + ((lane >> 4) << 3);
+        const int chunk = kk * 2 + ((lane >> 3) & 1);
+        ldmatrix_x4(b, sK[buf] + sw_off(row, chunk));
+        mma_16816(s[2 * jp], qf[kk], b[0], b[1]);
+        mma_16816(s[2 * jp + 1], qf[kk], b[2], b[3]);
+      }
+    }
+    // ---- mask + online softmax
+    const int kbase = kt * FA_BK;
+    const int qrow0 = q0 + warp * 16 + g;  // row for regs 0,1 ; +8 for regs 2,3
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = kbase + j * 8 + 2 * t + (e & 1);
+        const int qr = qrow0 + ((e >> 1) << 3);
+        bool ok = key < k_len;
+        if (p.causal) ok = ok && (key <= qr + causal_off);
+        const float v = ok ? s[j][e] * sl2 : -INFINITY;
+        s[j][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    }
+    float corr[2], mnew[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      mnew[r] = fmaxf(m_i[r], mx[r]);
+      const float msafe = (mnew[r] == -INFINITY) ? 0.f : mnew[r];
+      corr[r] = exp2f(m_i[r] - msafe);  // m_i = -inf -> 0
+      m_i[r] = mnew[r];
+      mnew[r] = msafe;
+      l_i[r] *= corr[r];
+    }
+    float rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pv = exp2f(s[j][e] - mnew[e >> 1]);
+        s[j][e] = pv;
+        rs[e >> 1] += pv;
+      }
+      o[j][0] *= corr[0]; o[j][1] *= corr[0]; o[j][2] *= corr[1]; o[j][3] *= corr[1];
+    }
+    l_i[0] += rs[0];
+    l_i[1] += rs[1];
+    // ---- O += P V
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step
+      uint32_t a[4];
+      a[0] = pack_half2(s[2 * kk][0], s[2 * kk][1]);
+      a[1] = pack_half2(s[2 * kk][2], s[2 * kk][3]);
+      a[2] = pack_half2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      a[3] = pack_half2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-wide output column tiles
+        uint32_t b[4];
+        const int row = kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+        const int chunk = jp * 2 + (lane >> 4);
+        ldmatrix_x4_trans(b, sV[buf] + sw_off(row, chunk));
+        mma_16816(o[2 * jp], a, b[0], b[1]);
+        mma_16816(o[2 * jp + 1], a, b[2], b[3]);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- finalize
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 1);
+    l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 2);
+  }
+  const float inv0 = l_i[0] > 0.f ? 1.f / l_i[0] : 0.f;
+  const float inv1 = l_i[1] > 0.f ? 1.f / l_i[1] : 0.f;
+  const int r0 = warp * 16 + g, r1 = r0 + 8;
+  __half* Og = p.O + (size_t)(p.q_start[seq] + q0) * p.ldo + head * HD;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = j * 8 + 2 * t;
+    if (r0 < q_valid) *reinterpret_cast<uint32_t*>(Og + (size_t)r0 * p.ldo + col) = pack_half2(o[j][0] * inv0, o[j][1] * inv0);
+    if (r1 < q_valid) *reinterpret_cast<uint32_t*>(Og + (size_t)r1 * p.ldo + col) = pack_half2(o[j][2] * inv1, o[j][3] * inv1);
+  }
+}
+
+int flash_attn(const AttnCall& c, cudaStream_t stream) {
+  if (c.n_seqs <= 0 || c.max_q <= 0) return M5_OK;
+  if ((c.ldq | c.ldk | c.ldv) % 8 != 0 || c.ldo % 2 != 0) return M5_ERR_ARG;
+  dim3 grid((c.max_q + FA_BQ - 1) / FA_BQ, c.n_heads, c.n_seqs);
+  flash_attn_kernel<<<grid, FA_THREADS, 0, stream>>>(c);
+  return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decode attention: one query per (row b, head h).  Grid (n_split, H, B); each CTA handles a contiguous
+// slice of the cached keys with 4 warps; every warp owns whole keys (lane = 2 of the 64 dims) so K/V rows are
+// read as fully coalesced 128-byte lines.  Partial (max, sum, acc[64]) per split are merged by a second kernel.
+static constexpr int DA_THREADS = 128;
+
+__global__ void __launch_bounds__(DA_THREADS)
+decode_attn_split_kernel(DecodeAttnCall p) {
+  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int L = p.kv_len[b];
+  const int per = (L + p.n_split - 1) / p.n_split;
+  const int k0 = split * per, k1 = min(L, k0 + per);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = p.H * HD;
+  const __half2 qh = *reinterpret_cast<const __half2*>(p.q + (size_t)b * D + h * HD + 2 * lane);
+  const float2 q = __half22float2(qh);
+  const float sl2 = 0.125f * 1.4426950408889634f;
+  const __half* kb = p.kc + ((size_t)b * p.W) * D + h * HD + 2 * lane;
+  const __half* vb = p.vc + ((size_t)b * p.W) * D + h * HD + 2 * lane;
+  float m = -INFINITY, l = 0.f, ax = 0.f, ay = 0.f;
+  // 4 keys in flight per warp iteration
+  for (int k = k0 + warp * 4; k < k1; k += 4 * 4) {
+    float sc[4];
+    float2 vv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int kk = k + u;
+      if (kk < k1) {
+        const float2 kf = __half22float2(*reinterpret_cast<const __half2*>(kb + (size_t)kk * D));
+        vv[u] = __half22float2(*reinterpret_cast<const __half2*>(vb + (size_t)kk * D));
+        sc[u] = q.x * kf.x + q.y * kf.y;
+      } else {
+        sc[u] = 0.f;
+        vv[u] = make_float2(0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float s = warp_sum(sc[u]);
+      if (k + u < k1) {
+        s *= sl2;
+        const float mn = fmaxf(m, s);
+        const float c = exp2f(m - mn);
+        const float pe = exp2f(s - mn);
+        l = l * c + pe;
+        ax = ax * c + pe * vv[u].x;
+        ay = ay * c + pe * vv[u].y;
+        m = mn;
+      }
+    }
+  }
+  // merge the 4 warps through smem
+  __shared__ float sm[4], sl[4], sa[4][HD];
+  if (lane == 0) { sm[warp] = m; sl[warp] = l; }
+  sa[warp][2 * lane] = ax;
+  sa[warp][2 * lane + 1] = ay;
+  __syncthreads();
+  if (warp == 0) {
+    float M = fmaxf(fmaxf(sm[0], sm[1]), fmaxf(sm[2], sm[3]));
+    float Ls = 0.f, ox = 0.f, oy = 0.f;
+    if (M > -INFINITY) {
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float c = exp2f(sm[w] - M);
+        Ls += sl[w] * c;
+        ox += sa[w][2 * lane] * c;
+        oy += sa[w][2 * lane + 1] * c;
+      }
+    }
+    float* sp = p.scratch + ((size_t)(b * p.H + h) * p.n_split + split) * (HD + 2);
+    if (lane == 0) { sp[0] = M; sp[1] = Ls; }
+    sp[2 + 2 * lane] = ox;
+    sp[2 + 2 * lane + 1] = oy;
+  }
+}
+
+__global__ void decode_attn_merge_kernel(DecodeAttnCall p) {
+  const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;  // 32 threads
+  const float* sp = p.scratch + ((size_t)(b * p.H + h) * p.n_split) * (HD + 2);
+  float M = -INFINITY;
+  for (int s = 0; s < p.n_split; ++s) M = fmaxf(M, sp[s * (HD + 2)]);
+  float L = 0.f, ox = 0.f, oy = 0.f;
+  for (int s = 0; s < p.n_split; ++s) {
+    const float* q = sp + s * (HD + 2);
+    if (q[0] == -INFINITY) continue;
+    const float c = exp2f(q[0] - M);
+    L += q[1] * c;
+    ox += q[2 + 2 * lane] * c;
+    oy += q[2 + 2 * lane + 1] * c;
+  }
+  const float inv = L > 0.f ? 1.f / L : 0.f;
+  *reinterpret_cast<__half2*>(p.out + (size_t)b * p.H * HD + h * HD + 2 * lane) = __floats2half2_rn(ox * inv, oy * inv);
+}
+
+size_t decode_attn_scratch_bytes(int B, int H, int n_split) { return (size_t)B * H * n_split * (HD + 2) * sizeof(float); }
+
+int decode_attn(const DecodeAttnCall& c, cudaStream_t stream) {
+  if (c.B <= 0) return M5_OK;
+  dim3 grid(c.n_split, c.H, c.B);
+  decode_attn_split_kernel<<<grid, DA_THREADS, 0, stream>>>(c);
+  dim3 g2(c.H, c.B);
+  decode_attn_merge_kernel<<<g2, 32, 0, stream>>>(c);
+  return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
+}
+
+}  // namespace m5

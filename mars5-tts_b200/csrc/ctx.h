@@ -1,0 +1,77 @@
+// Context object behind the C ABI: device, stream, weights (caller-owned device pointers), grow-only workspace arena.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "m5_internal.h"
+
+struct m5_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  m5_model_cfg cfg{};
+  std::map<std::string, m5_tensor> weights;
+  std::string last_error;
+  int64_t launches = 0;
+
+  // grow-only device arena, reset at the start of every public call
+  char* arena = nullptr;
+  size_t arena_cap = 0, arena_off = 0;
+  std::vector<void*> retired;  // older, smaller arenas kept until the call ends
+  // pinned host staging
+  char* pinned = nullptr;
+  size_t pinned_cap = 0;
+
+  // derived tables (device, fp32), built at create
+  float* rope_inv_freq = nullptr;  // [32]
+  float* pe_ar = nullptr;          // [max_pos, ar_dim]
+  float* pe_nar = nullptr;         // [max_pos, nar_dim]
+  float* twiddle = nullptr;        // iSTFT tables
+
+  int fail(int code, const std::string& msg) {
+    last_error = msg;
+    return code;
+  }
+};
+
+namespace m5 {
+
+struct Arena {
+  m5_ctx* c;
+  explicit Arena(m5_ctx* ctx) : c(ctx) {}
+  // Reserve total capacity up front (one cudaMalloc per high-water mark), then bump-allocate.
+  int reserve(size_t bytes);
+  template <typename T>
+  T* get(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    if (c->arena_off + bytes > c->arena_cap) return nullptr;
+    T* p = reinterpret_cast<T*>(c->arena + c->arena_off);
+    c->arena_off += bytes;
+    return p;
+  }
+};
+
+const m5_tensor* find_weight(m5_ctx* c, const std::string& name);
+template <typename T>
+inline const T* W(m5_ctx* c, const std::string& name) {
+  const m5_tensor* t = find_weight(c, name);
+  return t ? reinterpret_cast<const T*>(t->ptr) : nullptr;
+}
+
+#define M5_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return ctx->fail(M5_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));       \
+  } while (0)
+#define M5_TRY(call)                                                                           \
+  do {                                                                                         \
+    int _r = (call);                                                                           \
+    if (_r != M5_OK) {                                                                         \
+      if (ctx->last_error.empty()) ctx->last_error = std::string(#call) + " failed";           \
+      return _r;                                                                               \
+    }                                                                                          \
+  } while (0)
+
+}  // namespace m5

@@ -1,0 +1,91 @@
+// Internal declarations shared by the kernels and the C-ABI layer of libmars5_b200.so.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mars5_b200.h"
+
+namespace m5 {
+
+// ---- tcgen05 GEMM (gemm_tc5.cu) ----------------------------------------------------------------
+enum { M5_OUT_F32 = 0, M5_OUT_F16 = 1, M5_OUT_SWIGLU_F16 = 2, M5_OUT_F16_SPLIT = 3, M5_OUT_SWIGLU_F16_SPLIT = 4 };
+enum { M5_ACT_NONE = 0, M5_ACT_GELU = 1, M5_ACT_SILU = 2 };
+
+struct GemmCall {
+  const __half* A = nullptr;  // [M, K] row stride lda
+  const __half* W = nullptr;  // [N, K (or kwrap)] row stride ldw
+  int M = 0, N = 0, K = 0;
+  int lda = 0, ldw = 0;
+  int kwrap = 0;  // >0: split-precision A = [hi | lo], W re-read modulo kwrap
+  const float* bias = nullptr;
+  const float* colscale = nullptr;
+  void* out = nullptr;
+  void* out_lo = nullptr;
+  int ldc = 0;
+  int mode = M5_OUT_F32;
+  int act = M5_ACT_NONE;
+  int accumulate = 0;
+  int force_bn = 0;
+};
+int gemm_tc5(const GemmCall& g, cudaStream_t stream, int num_sms);
+
+// ---- skinny (M <= 32) weight-streaming GEMM for the AR decode step (gemm_skinny.cu) ------------
+struct SkinnyCall {
+  const __half* X = nullptr;  // [B, K] fp16 activations, row stride K
+  const __half* W = nullptr;  // [N, K] fp16
+  int B = 0, N = 0, K = 0;
+  float* out_f32 = nullptr;  // [B, ldc]; accumulate => out += result
+  __half* out_f16 = nullptr;  // swiglu mode: [B, N/2]
+  int ldc = 0;
+  int swiglu = 0;
+  int accumulate = 0;
+};
+int gemm_skinny(const SkinnyCall& c, cudaStream_t stream, int num_sms);
+
+// ---- row kernels (rowops.cu) -------------------------------------------------------------------
+// y = LayerNorm(x) (affine optional) or RMSNorm(x); x fp32 [M, D] -> fp16 [M, ldo] (+ optional lo halves and fp32 copy).
+struct NormCall {
+  const float* x = nullptr;
+  int M = 0, D = 0, ldx = 0;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;  // null for RMSNorm
+  float eps = 1e-5f;
+  int rms = 0;
+  __half* out = nullptr;
+  __half* out_lo = nullptr;  // optional
+  float* out_f32 = nullptr;  // optional
+  int ldo = 0;
+  const int* row_map = nullptr;  // optional: output row i reads input row row_map[i]
+};
+int norm_rows(const NormCall& c, cudaStream_t stream);
+
+// ---- attention (attention.cu) -------------------------------------------------------------------
+// Packed variable-length batch. Sequence s has queries at rows [q_start[s], q_start[s]+q_len[s]) of Q and keys at
+// rows [k_start[s], k_start[s]+k_len[s]) of K/V. head_dim is 64. Row strides in elements.
+struct AttnCall {
+  const __half* Q = nullptr; const __half* K = nullptr; const __half* V = nullptr;
+  int ldq = 0, ldk = 0, ldv = 0;
+  __half* O = nullptr; int ldo = 0;
+  int n_heads = 0, n_seqs = 0, max_q = 0;
+  const int* q_start = nullptr; const int* q_len = nullptr;
+  const int* k_start = nullptr; const int* k_len = nullptr;
+  int causal = 0;  // key j visible to query i iff j <= i + (k_len - q_len)
+  float scale = 0.125f;
+};
+int flash_attn(const AttnCall& c, cudaStream_t stream);
+
+// Single-query attention over the fp16 KV cache of the AR model (decode step).
+struct DecodeAttnCall {
+  const __half* q = nullptr;  // [B, H*64]
+  const __half* kc = nullptr; const __half* vc = nullptr;  // cache for this layer: [B, W, H*64]
+  int B = 0, H = 0, W = 0;
+  const int* kv_len = nullptr;  // [B] number of valid cached positions (including the current token)
+  __half* out = nullptr;        // [B, H*64]
+  float* scratch = nullptr;     // split workspace
+  int n_split = 1;
+};
+int decode_attn(const DecodeAttnCall& c, cudaStream_t stream);
+size_t decode_attn_scratch_bytes(int B, int H, int n_split);
+
+}  // namespace m5

@@ -1,0 +1,235 @@
+// Row-wise (HBM-bound) kernels: LayerNorm / RMSNorm producing the fp16 GEMM operand, RoPE + KV-cache append,
+// embedding gathers with sinusoidal position terms.  One warp per row, 128-bit loads, fp32 statistics.
+#include "m5_internal.h"
+#include "ptx.cuh"
+#include "rowops.h"
+
+namespace m5 {
+
+// ------------------------------------------------------------------------------------------------ norms
+// RMSNorm: nn_future.py:301-312 (x * rsqrt(mean(x^2) + eps) * weight, fp32).  LayerNorm: torch F.layer_norm
+// (biased variance, eps inside the sqrt), used with eps 4e-5 (model.py:13) and 1e-5 (heads, model.py:237).
+__global__ void __launch_bounds__(256) norm_rows_kernel(NormCall p) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.M) return;
+  const int src = p.row_map ? p.row_map[row] : row;
+  const float* x = p.x + (size_t)src * p.ldx;
+  const int D = p.D;
+  float s = 0.f, ss = 0.f;
+  for (int i = lane * 4; i < D; i += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(x + i);
+    s += v.x + v.y + v.z + v.w;
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  float mean = 0.f, rstd;
+  if (p.rms) {
+    rstd = rsqrtf(ss / D + p.eps);
+  } else {
+    mean = s / D;
+    // two-pass variance for accuracy (row is L1/L2 resident)
+    float vs = 0.f;
+    for (int i = lane * 4; i < D; i += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(x + i);
+      const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+      vs += a * a + b * b + c * c + d * d;
+    }
+    vs = warp_sum(vs);
+    rstd = rsqrtf(vs / D + p.eps);
+  }
+  for (int i = lane * 4; i < D; i += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(x + i);
+    float y[4] = {(v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd};
+    if (p.gamma) {
+      const float4 gm = *reinterpret_cast<const float4*>(p.gamma + i);
+      y[0] *= gm.x; y[1] *= gm.y; y[2] *= gm.z; y[3] *= gm.w;
+    }
+    if (p.beta) {
+      const float4 bt = *reinterpret_cast<const float4*>(p.beta + i);
+      y[0] += bt.x; y[1] += bt.y; y[2] += bt.z; y[3] += bt.w;
+    }
+    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ldo + i) = make_float4(y[0], y[1], y[2], y[3]);
+    if (p.out) {
+      const __half h0 = __float2half_rn(y[0]), h1 = __float2half_rn(y[1]), h2 = __float2half_rn(y[2]),
+                   h3 = __float2half_rn(y[3]);
+      __half2* o = reinterpret_cast<__half2*>(p.out + (size_t)row * p.ldo + i);
+      o[0] = __halves2half2(h0, h1);
+      o[1] = __halves2half2(h2, h3);
+      if (p.out_lo) {
+        __half2* ol = reinterpret_cast<__half2*>(p.out_lo + (size_t)row * p.ldo + i);
+        ol[0] = __floats2half2_rn(y[0] - __half2float(h0), y[1] - __half2float(h1));
+        ol[1] = __floats2half2_rn(y[2] - __half2float(h2), y[3] - __half2float(h3));
+      }
+    }
+  }
+}
+
+int norm_rows(const NormCall& c, cudaStream_t stream) {
+  if (c.M <= 0) return M5_OK;
+  if (c.D % 4 != 0 || c.ldx % 4 != 0 || c.ldo % 4 != 0) return M5_ERR_ARG;
+  const int wpb = 8;
+  norm_rows_kernel<<<(c.M + wpb - 1) / wpb, wpb * 32, 0, stream>>>(c);
+  return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------ fp32 -> fp16 rows
+__global__ void cast_rows_kernel(const float* x, int ldx, __half* o, __half* olo, int ldo, int M, int D,
+                                 const int* row_map) {
+  const size_t n = (size_t)M * (D / 4);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / (D / 4)), c = (int)(i % (D / 4)) * 4;
+    const int src = row_map ? row_map[row] : row;
+    const float4 v = *reinterpret_cast<const float4*>(x + (size_t)src * ldx + c);
+    const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
+    __half2* op = reinterpret_cast<__half2*>(o + (size_t)row * ldo + c);
+    op[0] = __halves2half2(h0, h1);
+    op[1] = __halves2half2(h2, h3);
+    if (olo) {
+      __half2* ol = reinterpret_cast<__half2*>(olo + (size_t)row * ldo + c);
+      ol[0] = __floats2half2_rn(v.x - __half2float(h0), v.y - __half2float(h1));
+      ol[1] = __floats2half2_rn(v.z - __half2float(h2), v.w - __half2float(h3));
+    }
+  }
+}
+int cast_rows(const float* x, int ldx, __half* o, __half* olo, int ldo, int M, int D, const int* row_map,
+              cudaStream_t stream) {
+  if (M <= 0) return M5_OK;
+  const size_t n = (size_t)M * (D / 4);
+  const int blocks = (int)min((size_t)148 * 8, (n + 255) / 256);
+  cast_rows_kernel<<<blocks, 256, 0, stream>>>(x, ldx, o, olo, ldo, M, D, row_map);
+  return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------ RoPE + KV append
+// Interleaved-pair RoPE (nn_future.py:166-198): (x[2i] + j x[2i+1]) * exp(j * pos * theta_i), theta_i = 10000^(-2i/64),
+// computed in fp32 and rounded back to fp16 (apply_rotary_emb's .type_as).  q is rotated in place inside the packed
+// qkv buffer; k (rotated) and v are scattered into the cache at [seq, pos] (nn_future.py:248-252; the window never
+// wraps because max_len < sliding_window, ar_generate.py:57).
+__global__ void rope_kv_kernel(__half* qkv, int ld, int n_rows, int H, const int* row_seq, const int* row_pos,
+                               __half* kc, __half* vc, int W, const float* inv_freq) {
+  const int D = H * 64;
+  const int pairs = D / 2;
+  const size_t total = (size_t)n_rows * pairs;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / pairs), pr = (int)(i % pairs);
+    const int pos = row_pos[row], seq = row_seq[row];
+    const int fi = pr & 31;
+    // angle in fp32 exactly as torch.outer(t, freqs).float() then polar (cos, sin of the fp32 product)
+    const float ang = (float)pos * inv_freq[fi];
+    float sn, cs;
+    sincosf(ang, &sn, &cs);
+    __half2* qp = reinterpret_cast<__half2*>(qkv + (size_t)row * ld) + pr;
+    const float2 q = __half22float2(*qp);
+    *qp = __floats2half2_rn(q.x * cs - q.y * sn, q.x * sn + q.y * cs);
+    const __half2* kp = reinterpret_cast<const __half2*>(qkv + (size_t)row * ld + D) + pr;
+    const float2 k = __half22float2(*kp);
+    const size_t coff = ((size_t)seq * W + pos) * D;
+    reinterpret_cast<__half2*>(kc + coff)[pr] = __floats2half2_rn(k.x * cs - k.y * sn, k.x * sn + k.y * cs);
+    reinterpret_cast<__half2*>(vc + coff)[pr] = reinterpret_cast<const __half2*>(qkv + (size_t)row * ld + 2 * D)[pr];
+  }
+}
+int rope_kv(__half* qkv, int ld, int n_rows, int H, const int* row_seq, const int* row_pos, __half* kc, __half* vc,
+            int W, const float* inv_freq, cudaStream_t stream) {
+  if (n_rows <= 0) return M5_OK;
+  const size_t total = (size_t)n_rows * H * 32;
+  const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
+  rope_kv_kernel<<<blocks, 256, 0, stream>>>(qkv, ld, n_rows, H, row_seq, row_pos, kc, vc, W, inv_freq);
+  return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
+}
+
+// Decode variant: the QKV projection of the skinny GEMM is fp32 [B, 3D]; round to fp16 first (autocast Linear output),
+// rotate, write q as fp16 [B, D] and append k, v at position pos[b] = len[b] - 1.
+__global__ void rope_kv_decode_kernel(const float* qkv, int B, int H, const int* len, __half* qout, __half* kc,
+                                      __half* vc, int W, const float* inv_freq, const int* active) {
+  const int D = H * 64, pairs = D / 2;
+  const int total = B * pairs;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / pairs, pr = i % pairs;
+    if (active && !active[b]) continue;
+    const int pos = len[b] - 1;
+    const float ang = (float)pos * inv_freq[pr & 31];
+    float sn, cs;
+    sincosf(ang, &sn, &cs);
+    const float* r = qkv + (size_t)b * 3 * D;
+    const float2 q = __half22float2(__floats2half2_rn(r[2 * pr], r[2 * pr + 1]));
+    const float2 k = __half22float2(__floats2half2_rn(r[D + 2 * pr], r[D + 2 * pr + 1]));
+    reinterpret_cast<__half2*>(qout + (size_t)b * D)[pr] = __floats2half2_rn(q.x * cs - q.y * sn, q.x * sn + q.y * cs);
+    const size_t coff = ((size_t)b * W + pos) * D;
+    reinterpret_cast<__half2*>(kc + coff)[pr] = __floats2half2_rn(k.x * cs - k.y * sn, k.x * sn + k.y * cs);
+    reinterpret_cast<__half2*>(vc + coff)[pr] = __floats2half2_rn(r[2 * D + 2 * pr], r[2 * D + 2 * pr + 1]);
+  }
+}
+int rope_kv_decode(const float* qkv, int B, int H, const int* len, __half* qout, __half* kc, __half* vc, int W,
+                   const float* inv_freq, const int* active, cudaStream_t stream) {
+  const int total = B * H * 32;
+  rope_kv_decode_kernel<<<(total + 255) / 256, 256, 0, stream>>>(qkv, B, H, len, qout, kc, vc, W, inv_freq, active);
+  return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------ embeddings
+// SinePositionalEmbedding (nn_future.py:35-83): x + alpha * pe[pos], pe[:,0::2]=sin(pos*div), pe[:,1::2]=cos(pos*div),
+// div_i = exp(2i * -(ln 1e4 / D)).  `pe` tables are precomputed on the host with torch-identical fp32 arithmetic.
+//
+// ChunkedEmbedding (model.py:147-159): concat over Q codebooks of emb_q[code_q] (dim D/Q each).
+// out[row] = (row is identity slot ? identity : chunked(codes[row])) + alpha * pe[pos] (+ add_vec)
+__global__ void chunked_embed_kernel(EmbedCall p) {
+  const int row = blockIdx.x;
+  const int src = p.code_row[row];
+  const int pos = p.pos[row];
+  const int D = p.D, dq = D / p.Q;
+  float* o = p.out + (size_t)row * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float v;
+    if (src < 0) {
+      v = p.identity[c];
+    } else {
+      const int qi = c / dq;
+      const int code = p.codes[(size_t)src * p.Q + qi];
+      v = __half2float(p.tables[((size_t)qi * p.n_codes + code) * dq + (c - qi * dq)]);
+    }
+    if (p.pe) v += p.alpha * p.pe[(size_t)pos * D + c];
+    if (p.add_vec) v += p.add_vec[c];
+    o[c] = v;
+  }
+}
+int chunked_embed(const EmbedCall& c, cudaStream_t stream) {
+  if (c.n_rows <= 0) return M5_OK;
+  chunked_embed_kernel<<<c.n_rows, 256, 0, stream>>>(c);
+  return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
+}
+
+// Token embedding rows: out[row] = (tok >= 0 ? table[tok] : vec_rows[-tok-1]) (+ alpha*pe[pos]) (+ add_vec)
+__global__ void token_embed_kernel(TokEmbedCall p) {
+  const int row = blockIdx.x;
+  const int tok = p.tok[row];
+  const int D = p.D;
+  float* o = p.out + (size_t)row * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float v = tok >= 0 ? __half2float(p.table[(size_t)tok * D + c]) : p.vec_rows[(size_t)(-tok - 1) * D + c];
+    if (p.pe) v += p.alpha * p.pe[(size_t)p.pos[row] * D + c];
+    if (p.add_vec) v += p.add_vec[c];
+    o[c] = v;
+  }
+}
+int token_embed(const TokEmbedCall& c, cudaStream_t stream) {
+  if (c.n_rows <= 0) return M5_OK;
+  token_embed_kernel<<<c.n_rows, 256, 0, stream>>>(c);
+  return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
+}
+
+// Gather rows: out[i] = x[idx[i]]  (fp32, D % 4 == 0)
+__global__ void gather_rows_kernel(const float* x, int ldx, const int* idx, float* out, int ldo, int n, int D) {
+  const int row = blockIdx.x;
+  const float* s = x + (size_t)idx[row] * ldx;
+  float* o = out + (size_t)row * ldo;
+  for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) *reinterpret_cast<float4*>(o + c) = *reinterpret_cast<const float4*>(s + c);
+}
+int gather_rows(const float* x, int ldx, const int* idx, float* out, int ldo, int n, int D, cudaStream_t stream) {
+  if (n <= 0) return M5_OK;
+  gather_rows_kernel<<<n, 128, 0, stream>>>(x, ldx, idx, out, ldo, n, D);
+  return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
+}
+
+}  // namespace m5
