@@ -39,12 +39,14 @@ typedef struct {
   /* AR CodecLM */
   int32_t ar_dim, ar_heads, ar_layers, ar_hidden, ar_vocab, ar_text_vocab, ar_spk_layers, ar_spk_ff;
   float ar_norm_eps;
+  float ar_pos_alpha; /* CodecLM.pos_embedding.alpha (learned scalar, nn_future.py:47) */
   /* NAR ResidualTransformer */
   int32_t nar_dim, nar_heads, nar_enc_layers, nar_dec_layers, nar_spk_layers, nar_ff, nar_text_vocab;
   int32_t n_classes; /* 1025 */
   int32_t n_quant;   /* 8 */
   float ln_eps;      /* 4e-5, model.py:13 */
   float head_ln_eps; /* 1e-5, model.py:237 */
+  float nar_pos_alpha, nar_cond_alpha, nar_ref_alpha; /* pos_embedding / cond_pos_embedding / ref_pos_embedding .alpha */
   /* Vocos encodec-24khz head */
   int32_t voc_feat, voc_dim, voc_inter, voc_layers, voc_nfft, voc_hop, voc_n_bw, voc_codebook;
   /* limits used to size workspaces */
@@ -105,6 +107,9 @@ typedef struct {
   int32_t q0_override_steps;
   int32_t deep_clone;
   int32_t precise;    /* 1: split-fp16 GEMM operands (fp32-class accuracy, 2x tensor work) */
+  /* optional HOST tables [4][T]: log_alpha, log_1_min_alpha, log_cumprod_alpha, log_1_min_cumprod_alpha
+   * (MultinomialDiffusion.__init__, diffuser.py:76-95); NULL -> computed inside the library */
+  const float* schedule;
 } m5_nar_cfg;
 
 /*
@@ -153,7 +158,9 @@ int m5_dbg_sample(m5_ctx* ctx, const float* logits, int32_t B, int32_t V, const 
                   const int32_t* hist, int32_t hist_stride, const int32_t* n_gen, const int32_t* n_phones,
                   const float* noise, uint64_t seed, int32_t* out_tok, float* out_logprobs);
 /* One reverse-diffusion posterior + sample (diffuser.py:359-393) from cond/uncond logits [R][8][K]. */
-int m5_dbg_posterior(m5_ctx* ctx, const float* cond, const float* uncond, int32_t R, int32_t t, int32_t T,
+/* sched6 (HOST): log_alpha[t], log_1_min_alpha[t], log_cumprod_alpha[t-1], log_1_min_cumprod_alpha[t-1],
+ *                log_cumprod_alpha[t], log_1_min_cumprod_alpha[t] */
+int m5_dbg_posterior(m5_ctx* ctx, const float* cond, const float* uncond, int32_t R, int32_t t, const float* sched6,
                      float guidance_w, float x0_temp, const int32_t* x_t, const int32_t* x_known, const uint8_t* mask,
                      const float* u_unknown, const float* u_known, uint64_t seed, int32_t* x_out);
 /* ISTFT head on [N][nfft+2] (mag-logits | phase) rows -> wav [hop*N] (Appendix C). */

@@ -15,10 +15,11 @@ ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
 
 class ModelCfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("ar_dim", "ar_heads", "ar_layers", "ar_hidden", "ar_vocab", "ar_text_vocab",
-                                         "ar_spk_layers", "ar_spk_ff")] + [("ar_norm_eps", C.c_float)] + \
+                                         "ar_spk_layers", "ar_spk_ff")] + [("ar_norm_eps", C.c_float), ("ar_pos_alpha", C.c_float)] + \
                [(n, C.c_int32) for n in ("nar_dim", "nar_heads", "nar_enc_layers", "nar_dec_layers", "nar_spk_layers",
                                          "nar_ff", "nar_text_vocab", "n_classes", "n_quant")] + \
-               [("ln_eps", C.c_float), ("head_ln_eps", C.c_float)] + \
+               [("ln_eps", C.c_float), ("head_ln_eps", C.c_float), ("nar_pos_alpha", C.c_float),
+                ("nar_cond_alpha", C.c_float), ("nar_ref_alpha", C.c_float)] + \
                [(n, C.c_int32) for n in ("voc_feat", "voc_dim", "voc_inter", "voc_layers", "voc_nfft", "voc_hop",
                                          "voc_n_bw", "voc_codebook", "max_pos")]
 
@@ -36,7 +37,8 @@ class ArCfg(C.Structure):
 
 class NarCfg(C.Structure):
     _fields_ = [("T", C.c_int32), ("x0_temp", C.c_float), ("guidance_w", C.c_float),
-                ("q0_override_steps", C.c_int32), ("deep_clone", C.c_int32), ("precise", C.c_int32)]
+                ("q0_override_steps", C.c_int32), ("deep_clone", C.c_int32), ("precise", C.c_int32),
+                ("schedule", C.c_void_p)]
 
 
 _P = C.c_void_p
@@ -59,7 +61,7 @@ _SIGS = {
     "m5_dbg_attn": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I]),
     "m5_dbg_decode_attn": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I]),
     "m5_dbg_sample": (_I, [_P, _P, _I, _I, C.POINTER(ArCfg), _I, _P, _I, _P, _P, _P, C.c_uint64, _P, _P]),
-    "m5_dbg_posterior": (_I, [_P, _P, _P, _I, _I, _I, C.c_float, C.c_float, _P, _P, _P, _P, _P, C.c_uint64, _P]),
+    "m5_dbg_posterior": (_I, [_P, _P, _P, _I, _I, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, C.c_uint64, _P]),
     "m5_dbg_istft": (_I, [_P, _P, _I, _P, _P]),
 }
 

@@ -200,6 +200,7 @@ static constexpr int DA_THREADS = 128;
 __global__ void __launch_bounds__(DA_THREADS)
 decode_attn_split_kernel(DecodeAttnCall p) {
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  if (p.done && p.done[b]) return;
   const int L = p.kv_len[b];
   const int per = (L + p.n_split - 1) / p.n_split;
   const int k0 = split * per, k1 = min(L, k0 + per);
@@ -269,6 +270,7 @@ decode_attn_split_kernel(DecodeAttnCall p) {
 
 __global__ void decode_attn_merge_kernel(DecodeAttnCall p) {
   const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;  // 32 threads
+  if (p.done && p.done[b]) return;
   const float* sp = p.scratch + ((size_t)(b * p.H + h) * p.n_split) * (HD + 2);
   float M = -INFINITY;
   for (int s = 0; s < p.n_split; ++s) M = fmaxf(M, sp[s * (HD + 2)]);

@@ -56,7 +56,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 template <int BLOCK_N>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N,
-                int K, int kwrap, GemmEpi epi) {
+                int K, int kwrap, int awrap, GemmEpi epi) {
   using S = GemmSmem<BLOCK_N>;
   constexpr int STAGES = S::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -117,7 +117,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           uint8_t* sb = sa + S::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
           const int k0 = kb * BLOCK_K;
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m_blk * BLOCK_M);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], awrap > 0 ? (k0 % awrap) : k0, m_blk * BLOCK_M);
           tma_load_2d(sb, &tmap_b, &full_bar[stage], kwrap > 0 ? (k0 % kwrap) : k0, n_blk * BLOCK_N);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -171,6 +171,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         const int col0 = n_blk * BLOCK_N + c * 32;
         if (col0 >= N) break;  // warp-uniform
+        __syncwarp();          // reconverge before the warp-collective TMEM load
         uint32_t r[32];
         tc5_ld_32x32(taddr0 + c * 32, r);
         tc5_wait_ld();
@@ -307,7 +308,7 @@ template <int BLOCK_N>
 static int launch_bn(const GemmCall& g, cudaStream_t stream, int num_sms) {
   using S = GemmSmem<BLOCK_N>;
   CUtensorMap ta, tb;
-  const int Ka = g.K;                          // A's K extent (2*kwrap in split mode)
+  const int Ka = g.awrap > 0 ? g.awrap : g.K;   // A's stored K extent
   const int Kb = g.kwrap > 0 ? g.kwrap : g.K;  // W's K extent
   if (make_tmap(&ta, g.A, g.M, Ka, g.lda, BLOCK_M) != M5_OK) return M5_ERR_CUDA;
   if (make_tmap(&tb, g.W, g.N, Kb, g.ldw, BLOCK_N) != M5_OK) return M5_ERR_CUDA;
@@ -324,7 +325,7 @@ static int launch_bn(const GemmCall& g, cudaStream_t stream, int num_sms) {
   GemmEpi e;
   e.bias = g.bias; e.colscale = g.colscale; e.out = g.out; e.out_lo = g.out_lo; e.ldc = g.ldc;
   e.mode = g.mode; e.act = g.act; e.accumulate = g.accumulate;
-  gemm_tc5_kernel<BLOCK_N><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ta, tb, g.M, g.N, g.K, g.kwrap, e);
+  gemm_tc5_kernel<BLOCK_N><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ta, tb, g.M, g.N, g.K, g.kwrap, g.awrap, e);
   return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
 }
 

@@ -1,0 +1,63 @@
+// Host-side composition of kernels into the transformer blocks shared by the AR speaker encoder, the NAR speaker
+// encoder, the NAR encoder (nn.TransformerEncoderLayer, norm_first, FNNSwiGLU activation with linear1 = Identity;
+// model.py:56-67,179-199) and the NAR decoder (nn.TransformerDecoderLayer, model.py:186-193).
+#pragma once
+#include <string>
+
+#include "ctx.h"
+#include "rowops.h"
+
+namespace m5 {
+
+// A packed batch of sequences living in DEVICE int arrays (+ host copies of the extents).
+struct SeqSet {
+  int n = 0;          // sequences
+  int rows = 0;       // total rows
+  int max_len = 0;    // longest sequence
+  const int* start = nullptr;  // device [n]
+  const int* len = nullptr;    // device [n]
+  const int* klen = nullptr;   // device [n] optional: visible keys per sequence (key-padding mask), default = len
+};
+
+struct EncLayerW {
+  const float *n1w, *n1b, *n2w, *n2b;
+  const __half* in_w; const float* in_b;    // [3D, D]
+  const __half* out_w; const float* out_b;  // [D, D]
+  const __half* wv;                         // [2*ff, D] rows interleaved (W_j, V_j)
+  const __half* w2; const float* b2;        // [D, ff]
+};
+struct DecLayerW {
+  const float *n1w, *n1b, *n2w, *n2b, *n3w, *n3b;
+  const __half* sa_in_w; const float* sa_in_b; const __half* sa_out_w; const float* sa_out_b;
+  const __half* ca_q_w; const float* ca_q_b;      // [D, D]
+  const __half* ca_kv_w; const float* ca_kv_b;    // [2D, D]
+  const __half* ca_out_w; const float* ca_out_b;
+  const __half* wv; const __half* w2; const float* b2;
+};
+int load_enc_layer(m5_ctx* ctx, const std::string& prefix, EncLayerW& w);
+int load_dec_layer(m5_ctx* ctx, const std::string& prefix, DecLayerW& w);
+
+// Scratch shared by the blocks (sized for `rows` rows by the caller).
+struct BlockScratch {
+  __half* h16 = nullptr;    // [rows, 2*D]   normalised activations (hi | lo when precise)
+  __half* qkv16 = nullptr;  // [rows, 3*D]
+  __half* att16 = nullptr;  // [rows, D]
+  __half* g16 = nullptr;    // [rows, 2*ff]  gated activations (hi | lo when precise)
+  __half* kv16 = nullptr;   // [mem_rows, 2*D] cross-attention keys/values
+};
+size_t block_scratch_bytes(int rows, int mem_rows, int D, int ff);
+void block_scratch_carve(Arena& a, BlockScratch& s, int rows, int mem_rows, int D, int ff);
+
+// x (fp32 [rows, D]) is updated in place.
+int encoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const EncLayerW& w, int D, int H, int ff, float eps,
+                  bool precise, const BlockScratch& s);
+// mem16: encoder output after its final LayerNorm as fp16 [mem rows, D*(precise?2:1)]
+int decoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const __half* mem16, const SeqSet& mem_seqs,
+                  const DecLayerW& w, int D, int H, int ff, float eps, bool precise, const BlockScratch& s);
+
+// convenience wrappers that count launches
+int run_gemm(m5_ctx* ctx, const GemmCall& g);
+int run_norm(m5_ctx* ctx, const NormCall& n);
+int run_attn(m5_ctx* ctx, const AttnCall& a);
+
+}  // namespace m5

@@ -17,7 +17,8 @@ struct GemmCall {
   const __half* W = nullptr;  // [N, K (or kwrap)] row stride ldw
   int M = 0, N = 0, K = 0;
   int lda = 0, ldw = 0;
-  int kwrap = 0;  // >0: split-precision A = [hi | lo], W re-read modulo kwrap
+  int kwrap = 0;  // >0: W k-coordinate wraps modulo kwrap (A = [hi | lo] against one copy of W)
+  int awrap = 0;  // >0: A k-coordinate wraps modulo awrap (A = [hi | lo] against W = [W_hi | W_hi | W_lo])
   const float* bias = nullptr;
   const float* colscale = nullptr;
   void* out = nullptr;
@@ -81,6 +82,7 @@ struct DecodeAttnCall {
   const __half* kc = nullptr; const __half* vc = nullptr;  // cache for this layer: [B, W, H*64]
   int B = 0, H = 0, W = 0;
   const int* kv_len = nullptr;  // [B] number of valid cached positions (including the current token)
+  const int* done = nullptr;    // [B] optional: rows that already stopped are skipped
   __half* out = nullptr;        // [B, H*64]
   float* scratch = nullptr;     // split workspace
   int n_split = 1;

@@ -15,6 +15,7 @@
 //   8. EOS stops the row without being appended (ar_generate.py:121-135).
 #include "sampler.h"
 
+#include "philox.cuh"
 #include "ptx.cuh"
 
 namespace m5 {
@@ -24,25 +25,6 @@ __device__ __forceinline__ uint32_t fkey(float f) {
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-__device__ __forceinline__ uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t* hi) {
-  const uint64_t p = (uint64_t)a * b;
-  *hi = (uint32_t)(p >> 32);
-  return (uint32_t)p;
-}
-// Philox4x32-10; returns 4 x 32 random bits for (key, counter).
-__device__ void philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0, hi1;
-    const uint32_t lo0 = mulhilo(0xD2511F53u, c0, &hi0);
-    const uint32_t lo1 = mulhilo(0xCD9E8D57u, c2, &hi1);
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
 __device__ float philox_uniform(uint64_t seed, uint64_t stream, uint32_t step, uint32_t idx) {
   uint32_t o[4];
   philox4x32((uint32_t)seed, (uint32_t)(seed >> 32), idx, step, (uint32_t)stream, (uint32_t)(stream >> 32), o);

@@ -1,0 +1,310 @@
+"""Host-side mirror of the reference interface for the hot path.
+
+* ``Engine``      -- thin, typed wrapper over the C ABI (include/mars5_b200.h): batches of independent utterances in,
+                     ids / codes / waveforms out.  All arithmetic happens in libmars5_b200.so; this file only packs
+                     pointers.  There is no PyTorch/CPU fallback: a missing library or GPU raises.
+* ``InferenceConfig`` / ``Mars5TTS`` -- drop-in for /root/reference/inference.py:24-77 and :80-307
+                     (same constructor inputs ``ar_ckpt`` / ``nar_ckpt``, same ``tts()`` / ``vocode()`` signatures and
+                     return values).  Tokenisers and the Encodec encoder are outside the hot path (SURVEY.md section 2 rows
+                     10-11); they are taken from the reference package when it is importable or injected by the caller.
+"""
+import ctypes as C
+import logging
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import capi, weights
+
+
+@dataclass
+class InferenceConfig:
+    """Same fields and defaults as the reference's InferenceConfig (inference.py:24-77)."""
+    temperature: float = 0.7
+    top_k: int = 200
+    top_p: float = 0.2
+    typical_p: float = 1.0
+    freq_penalty: float = 3
+    presence_penalty: float = 0.4
+    rep_penalty_window: int = 80
+    eos_penalty_decay: float = 0.5
+    eos_penalty_factor: float = 1
+    eos_estimated_gen_length_factor: float = 1.0
+    timesteps: int = 200
+    x_0_temp: float = 0.7
+    q0_override_steps: int = 20
+    nar_guidance_w: float = 3
+    max_prompt_dur: float = 12
+    generate_max_len_override: int = -1
+    deep_clone: bool = True
+    use_kv_cache: bool = True
+    trim_db: float = 27
+    beam_width: int = 1
+    ref_audio_pad: float = 0
+
+
+def _i32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+
+
+def _cat_i32(arrs, width=None):
+    if len(arrs) == 0:
+        return np.zeros((0,) if width is None else (0, width), dtype=np.int32)
+    return np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.int32).reshape(-1) if width is None
+                                                else np.asarray(a, dtype=np.int32).reshape(-1, width) for a in arrs]))
+
+
+class Engine:
+    """One context on one GPU.  `tensors` (already-repacked CPU tensors) may be given to skip the repack (multi-GPU:
+    rank 0 repacks, the blob is broadcast over NCCL, see dist.py)."""
+
+    def __init__(self, ar_sd=None, nar_sd=None, voc_sd=None, text_vocab_len=None, device=0, max_pos=4096,
+                 packed=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("mars5_tts_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = capi.load()
+        self.device = int(device)
+        if packed is None:
+            dims = weights.dims_from_state(ar_sd, nar_sd, voc_sd, text_vocab_len)
+            tensors, alphas = weights.repack(ar_sd, nar_sd, voc_sd, dims, max_pos=max_pos)
+            packed = {"dims": dims, "alphas": alphas, "tensors": tensors, "max_pos": max_pos}
+        self.dims, self.alphas = packed["dims"], packed["alphas"]
+        dev = torch.device("cuda", self.device)
+        self.tensors = {k: (v if v.is_cuda else v.to(dev)) for k, v in packed["tensors"].items()}
+        self.cfg = weights.make_cfg(self.dims, self.alphas, packed["max_pos"])
+        arr = (capi.Tensor * len(self.tensors))()
+        self._names = []
+        for i, (k, v) in enumerate(self.tensors.items()):
+            nm = k.encode()
+            self._names.append(nm)
+            arr[i].name, arr[i].ptr, arr[i].numel = nm, v.data_ptr(), v.numel()
+            arr[i].dtype = capi.DT_F16 if v.dtype == torch.float16 else capi.DT_F32
+        self.ctx = C.c_void_p()
+        rc = self.lib.m5_create(self.device, C.byref(self.cfg), arr, len(self.tensors), C.byref(self.ctx))
+        if rc != 0:
+            raise capi.M5Error(f"m5_create failed with code {rc}")
+        self._sched_cache = {}
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.m5_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(self.lib.m5_launch_count(self.ctx))
+
+    # ------------------------------------------------------------------------------------------ AR
+    def make_ar_cfg(self, icfg: InferenceConfig, max_len, eos_id, force_len=0, sync_every=16):
+        c = capi.ArCfg()
+        c.temperature, c.top_k, c.top_p = icfg.temperature, icfg.top_k, icfg.top_p
+        c.alpha_frequency, c.alpha_presence, c.penalty_window = icfg.freq_penalty, icfg.presence_penalty, icfg.rep_penalty_window
+        c.eos_penalty_decay, c.eos_penalty_factor = icfg.eos_penalty_decay, icfg.eos_penalty_factor
+        c.max_len, c.eos_id, c.force_len, c.sync_every = max_len, eos_id, force_len, sync_every
+        return c
+
+    def ar_generate(self, prompts, spk_codes, n_phones, ar_cfg, noise=None, seed=0, utt_ids=None, dump_steps=0):
+        """prompts: list of int sequences; spk_codes: list of (Pf, 8) arrays.  Host buffers (mem = HOST).
+        Returns (list of id arrays, hit_maxlen list, logits dump or None)."""
+        B = len(prompts)
+        ids, plen = _cat_i32(prompts), _i32([len(p) for p in prompts])
+        codes, slen = _cat_i32(spk_codes, 8), _i32([len(s) for s in spk_codes])
+        nph = _i32(n_phones) if n_phones is not None else None
+        V, max_len = self.dims["ar_vocab"], ar_cfg.max_len
+        out_ids = np.zeros((B, max_len), dtype=np.int32)
+        out_len, hit = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+        noise_np, nsteps = None, 0
+        if noise is not None:
+            noise_np = np.ascontiguousarray(np.asarray(noise, dtype=np.float32))
+            nsteps = noise_np.shape[1]
+        dump = np.zeros((B, dump_steps, V), dtype=np.float32) if dump_steps else None
+        utt = np.ascontiguousarray(np.asarray(utt_ids, dtype=np.int64)) if utt_ids is not None else None
+        rc = self.lib.m5_ar_generate(self.ctx, B, capi.ptr(ids), capi.ptr(plen), capi.ptr(codes), capi.ptr(slen),
+                                     capi.ptr(nph), C.byref(ar_cfg), capi.MEM_HOST, capi.ptr(noise_np), nsteps,
+                                     C.c_uint64(seed), capi.ptr(utt), capi.ptr(out_ids), capi.ptr(out_len), capi.ptr(hit),
+                                     capi.ptr(dump), dump_steps)
+        capi.check(self.ctx, rc, "m5_ar_generate")
+        return [out_ids[b, :out_len[b]].copy() for b in range(B)], hit.tolist(), dump
+
+    def ar_forward(self, prompts, spk_codes):
+        B = len(prompts)
+        ids, plen = _cat_i32(prompts), _i32([len(p) for p in prompts])
+        codes, slen = _cat_i32(spk_codes, 8), _i32([len(s) for s in spk_codes])
+        V = self.dims["ar_vocab"]
+        out = np.zeros((int(plen.sum()), V), dtype=np.float32)
+        rc = self.lib.m5_ar_forward(self.ctx, B, capi.ptr(ids), capi.ptr(plen), capi.ptr(codes), capi.ptr(slen),
+                                    capi.MEM_HOST, capi.ptr(out))
+        capi.check(self.ctx, rc, "m5_ar_forward")
+        offs = np.concatenate([[0], np.cumsum(plen)])
+        return [out[offs[b]:offs[b + 1]] for b in range(B)]
+
+    # ------------------------------------------------------------------------------------------ NAR
+    def schedule(self, T):
+        if T not in self._sched_cache:
+            self._sched_cache[T] = np.ascontiguousarray(weights.diffusion_schedule(T).numpy())
+        return self._sched_cache[T]
+
+    def make_nar_cfg(self, icfg: InferenceConfig, T=200, precise=False):
+        c = capi.NarCfg()
+        c.T, c.x0_temp, c.guidance_w = T, icfg.x_0_temp, icfg.nar_guidance_w
+        c.q0_override_steps, c.deep_clone, c.precise = icfg.q0_override_steps, int(icfg.deep_clone), int(precise)
+        c.schedule = self.schedule(T).ctypes.data
+        return c
+
+    def nar_infer(self, c_text, c_codes, x_l0, nar_cfg, x_init=None, noise=None, seed=0, utt_ids=None):
+        B = len(c_text)
+        text, tlen = _cat_i32(c_text), _i32([len(t) for t in c_text])
+        codes, clen = _cat_i32(c_codes, 8), _i32([len(c) for c in c_codes])
+        l0, xlen = _cat_i32(x_l0), _i32([len(x) for x in x_l0])
+        xi = _cat_i32(x_init, 8) if x_init is not None else None
+        nz = np.ascontiguousarray(np.asarray(noise, dtype=np.float32)) if noise is not None else None
+        utt = np.ascontiguousarray(np.asarray(utt_ids, dtype=np.int64)) if utt_ids is not None else None
+        out = np.zeros((int(xlen.sum()), 8), dtype=np.int32)
+        rc = self.lib.m5_nar_infer(self.ctx, B, capi.ptr(text), capi.ptr(tlen), capi.ptr(codes), capi.ptr(clen),
+                                   capi.ptr(l0), capi.ptr(xlen), C.byref(nar_cfg), capi.MEM_HOST, capi.ptr(xi),
+                                   capi.ptr(nz), C.c_uint64(seed), capi.ptr(utt), capi.ptr(out))
+        capi.check(self.ctx, rc, "m5_nar_infer")
+        offs = np.concatenate([[0], np.cumsum(xlen)])
+        return [out[offs[b]:offs[b + 1]] for b in range(B)]
+
+    def nar_forward(self, c_text, c_codes, x, t, drop_cond=False, precise=False):
+        B = len(c_text)
+        text, tlen = _cat_i32(c_text), _i32([len(v) for v in c_text])
+        codes, clen = _cat_i32(c_codes, 8), _i32([len(v) for v in c_codes])
+        xs, xlen = _cat_i32(x, 8), _i32([len(v) for v in x])
+        K = self.dims["n_classes"]
+        out = np.zeros((int(xlen.sum()), 8, K), dtype=np.float32)
+        rc = self.lib.m5_nar_forward(self.ctx, B, capi.ptr(text), capi.ptr(tlen), capi.ptr(codes), capi.ptr(clen),
+                                     capi.ptr(xs), capi.ptr(xlen), int(t), int(drop_cond), int(precise), capi.MEM_HOST,
+                                     capi.ptr(out))
+        capi.check(self.ctx, rc, "m5_nar_forward")
+        offs = np.concatenate([[0], np.cumsum(xlen)])
+        return [out[offs[b]:offs[b + 1]] for b in range(B)]
+
+    # ------------------------------------------------------------------------------------------ vocoder
+    def vocode(self, codes, bandwidth_id=1):
+        B = len(codes)
+        cs, nf = _cat_i32(codes, 8), _i32([len(c) for c in codes])
+        hop = self.dims["voc_hop"]
+        out = np.zeros(int(nf.sum()) * hop, dtype=np.float32)
+        rc = self.lib.m5_vocode(self.ctx, B, capi.ptr(cs), capi.ptr(nf), int(bandwidth_id), capi.MEM_HOST, capi.ptr(out))
+        capi.check(self.ctx, rc, "m5_vocode")
+        offs = np.concatenate([[0], np.cumsum(nf)]) * hop
+        return [out[offs[b]:offs[b + 1]] for b in range(B)]
+
+
+class Mars5TTS:
+    """Drop-in for the reference's Mars5TTS (inference.py:79-307) on the hot path.
+
+    ``ar_ckpt`` / ``nar_ckpt``: the dicts hubconf.py builds ({'vocab': {...}, 'model': state_dict}).  The text /
+    speech tokenisers are built from ``ar_ckpt['vocab']`` with the reference's minbpe when it is importable, or passed
+    in (``texttok`` / ``speechtok``); ``codec`` must offer ``encode(wav[None]) -> [(codes (1, 8, T), scale)]`` like
+    EncodecModel; ``vocos_state`` is the state dict of Vocos("charactr/vocos-encodec-24khz") (weight-norm removed).
+    """
+
+    def __init__(self, ar_ckpt, nar_ckpt, device: Optional[str] = None, *, vocos_state=None, texttok=None,
+                 speechtok=None, codec=None):
+        if texttok is None or speechtok is None:
+            import io
+            from mars5.minbpe.codebook import CodebookTokenizer  # reference package (pure-Python, out of scope)
+            from mars5.minbpe.regex import GPT4_SPLIT_PATTERN, RegexTokenizer
+            texttok = RegexTokenizer(GPT4_SPLIT_PATTERN)
+            texttok.load(io.BytesIO(ar_ckpt["vocab"]["texttok.model"].encode("utf-8")))
+            speechtok = CodebookTokenizer(GPT4_SPLIT_PATTERN)
+            speechtok.load(io.BytesIO(ar_ckpt["vocab"]["speechtok.model"].encode("utf-8")))
+        self.texttok, self.speechtok, self.codec = texttok, speechtok, codec
+        dev_index = torch.device(device).index if device not in (None, "cuda") else None
+        self.device = torch.device("cuda", dev_index or 0)
+        self.engine = Engine(ar_ckpt["model"], nar_ckpt["model"], vocos_state, len(texttok.vocab), device=self.device.index)
+        self.n_vocab = len(texttok.vocab) + len(speechtok.vocab)
+        self.n_text_vocab = len(texttok.vocab) + 1
+        self.diffusion_n_classes = 1025
+        self.default_T = 200
+        self.sr, self.latent_sr = 24000, 75
+
+    @torch.inference_mode()
+    def vocode(self, tokens: torch.Tensor) -> torch.Tensor:
+        """tokens (seq_len, n_q) -> (1, T) float CPU tensor, bandwidth_id = 1 like the reference (inference.py:165-171)."""
+        wav = self.engine.vocode([tokens.detach().cpu().numpy()], bandwidth_id=1)[0]
+        return torch.from_numpy(wav)[None]
+
+    def _prepare(self, text, ref_audio, ref_transcript, cfg):
+        """Host glue of inference.py:212-258: tokenise, encode the reference clip, build the AR prompt."""
+        if cfg.deep_clone and ref_transcript is None:
+            raise AssertionError("Inference config deep clone is set to true, but reference transcript not specified! "
+                                 "Please specify the transcript of the prompt, or set deep_clone=False in the inference `cfg` argument.")
+        if ref_audio.shape[-1] / self.sr > cfg.max_prompt_dur:
+            logging.warning("Reference audio duration is > max suggested ref audio. Expect quality degradations.")
+        tt = self.texttok
+        text_tokens = tt.encode("<|startoftext|>" + text.strip() + "<|endoftext|>", allowed_special="all")
+        if ref_audio.dim() == 1:
+            ref_audio = ref_audio[None]
+        if ref_audio.shape[0] != 1:
+            ref_audio = ref_audio.mean(dim=0, keepdim=True)
+        ref_audio = torch.nn.functional.pad(ref_audio, (int(self.sr * cfg.ref_audio_pad), 0))
+        prompt_codec = self.codec.encode(ref_audio[None])[0][0]  # (1, n_q, T)
+        l0 = prompt_codec[0, 0].tolist()
+        speech_tokens = self.speechtok.encode(" ".join(str(t) for t in l0).strip())
+        spk_ref = prompt_codec[0].T.cpu().numpy().astype(np.int32)  # (T, n_q)
+        offset_codes = [p + len(tt.vocab) for p in speech_tokens]
+        n_speech_inp = 0
+        if not cfg.deep_clone:
+            offset_codes = offset_codes[:0]
+        else:
+            text_tokens = tt.encode("<|startoftext|>" + ref_transcript + " " + str(text).strip() + "<|endoftext|>",
+                                    allowed_special="all")
+            n_speech_inp = len(offset_codes)
+        prompt = text_tokens + offset_codes
+        first_codec_idx = len(prompt) - n_speech_inp + 1
+        return dict(prompt=prompt, first_codec_idx=first_codec_idx, text_tokens=text_tokens, spk_ref=spk_ref,
+                    n_phones=round(cfg.eos_estimated_gen_length_factor * len(text)))
+
+    @torch.inference_mode()
+    def tts_batch(self, texts: List[str], ref_audios, ref_transcripts, cfg: InferenceConfig = InferenceConfig(),
+                  seed: int = 0):
+        """Batched tts(): every row equals a single reference call.  Returns a list of (L0 codes, waveform)."""
+        assert cfg.beam_width == 1, "Only beam size of 1 is currently supported."
+        preps = [self._prepare(t, a, r, cfg) for t, a, r in zip(texts, ref_audios, ref_transcripts)]
+        eng, tt = self.engine, self.texttok
+        max_len = cfg.generate_max_len_override if cfg.generate_max_len_override > 1 else 2000
+        eos = len(tt.vocab) + self.speechtok.special_tokens["<|endofspeech|>"]
+        results = [None] * len(preps)
+        for s in range(0, len(preps), 32):  # the AR kernels keep <= 32 rows in flight
+            chunk = preps[s:s + 32]
+            acfg = eng.make_ar_cfg(cfg, max_len, eos)
+            ids, hit, _ = eng.ar_generate([p["prompt"] for p in chunk], [p["spk_ref"] for p in chunk],
+                                          [p["n_phones"] for p in chunk], acfg, seed=seed,
+                                          utt_ids=list(range(s, s + len(chunk))))
+            l0s = []
+            for p, seq, h in zip(chunk, ids, hit):
+                if h:
+                    logging.warning(f"[autoregressive generation] output length = {len(seq)} -- inference likely failed or input too long!")
+                toks = np.clip(seq.astype(np.int64) - len(tt.vocab), 0, None)[p["first_codec_idx"]:].tolist()
+                l0s.append(np.asarray([c for c in self.speechtok.decode_int(toks) if type(c) == int], dtype=np.int32))
+            ncfg = eng.make_nar_cfg(cfg, T=self.default_T)
+            codes = eng.nar_infer([p["text_tokens"] for p in chunk], [p["spk_ref"] for p in chunk], l0s, ncfg, seed=seed,
+                                  utt_ids=list(range(s, s + len(chunk))))
+            outs = []
+            for p, c in zip(chunk, codes):
+                skip = len(p["spk_ref"]) if cfg.deep_clone else 0  # second crop of inference.py:300-301
+                outs.append(c[skip:])
+            wavs = eng.vocode(outs, bandwidth_id=1)
+            for i, (l0, w) in enumerate(zip(l0s, wavs)):
+                results[s + i] = (torch.from_numpy(l0.astype(np.int64)).to(self.device), torch.from_numpy(w))
+        return results
+
+    @torch.inference_mode()
+    def tts(self, text: str, ref_audio: torch.Tensor, ref_transcript: Optional[str] = None,
+            cfg: Optional[InferenceConfig] = InferenceConfig()):
+        """Same contract as the reference's tts() (inference.py:201-307) minus the CPU silence trim (mars5/trim.py is
+        outside the hot path and broken under numpy 2; apply it to the returned audio if wanted)."""
+        codes, wav = self.tts_batch([text], [ref_audio], [ref_transcript], cfg)[0]
+        return codes, wav

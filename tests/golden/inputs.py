@@ -1,0 +1,42 @@
+"""Replays the seeded input draws of make_golden.py (same generator, same order) so that the big random tensors need
+not be stored in the fixture.  Keep in lock-step with make_golden.py; the fixture's chk_* sums guard against drift."""
+import torch
+
+from mars5_tts_b200 import synth
+
+
+def make_inputs():
+    size = synth.TINY
+    n_text = 258
+    V = n_text + 1025
+    g = torch.Generator().manual_seed(1234)
+    d = {}
+    Pf, n_txt, n_sp = 12, 9, 5
+    d["ar_spk"] = torch.randint(0, 1024, (Pf, 8), generator=g)
+    text_ids = [256] + torch.randint(0, 256, (n_txt,), generator=g).tolist() + [257]
+    speech_ids = (torch.randint(0, 1024, (n_sp,), generator=g) + n_text).tolist()
+    d["ar_text_ids"], d["ar_prompt"] = text_ids, torch.tensor(text_ids + speech_ids)
+    steps = 14
+    d["ar_max_len"] = len(d["ar_prompt"]) + 14
+    d["ar_noise"] = torch.empty(steps, V).exponential_(1, generator=g)
+    d["smp_logits"] = torch.randn(3, V, generator=g) * 3
+    d["smp_prev"] = torch.randint(n_text, V, (3, 30), generator=g)
+    Tc, S = 11, 19
+    d["nar_c_text"] = torch.randint(0, n_text, (Tc,), generator=g)
+    d["nar_c_codes"] = torch.randint(0, 1024, (Pf, 8), generator=g)
+    d["nar_x"] = torch.randint(0, 1025, (S, 8), generator=g)
+    T, N = 6, 7
+    d["nar_loop_T"] = T
+    d["nar_loop_x_l0"] = torch.randint(0, 1024, (N,), generator=g)
+    d["nar_loop_x_init"] = torch.randint(0, 1025, (N, 8), generator=g)
+    d["nar_loop_deep_u"] = torch.rand(T, 2, N + Pf, 8, 1025, generator=g)
+    d["nar_loop_shallow_u"] = torch.rand(T, 2, N, 8, 1025, generator=g)
+    Sx = 9
+    d["post_cond"] = torch.randn(Sx, 8, 1025, generator=g) * 2
+    d["post_uncond"] = torch.randn(Sx, 8, 1025, generator=g) * 2
+    d["post_xt"] = torch.randint(0, 1025, (Sx, 8), generator=g)
+    d["post_xk"] = torch.randint(0, 1024, (Sx, 8), generator=g)
+    d["post_m"] = torch.rand(Sx, 8, generator=g) < 0.4
+    d["post_u"] = torch.rand(2, Sx, 8, 1025, generator=g)
+    d["size"], d["n_text"], d["V"], d["eos"] = size, n_text, V, n_text + 1024
+    return d
