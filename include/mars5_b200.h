@@ -68,6 +68,13 @@ int m5_sync(m5_ctx* ctx);
 /* Number of kernels this library launched on ctx's stream since creation (bench.py's gpu_launches). */
 int64_t m5_launch_count(m5_ctx* ctx);
 int m5_num_sms(m5_ctx* ctx);
+/* cudaStream_t the context enqueues on (for the caller's CUDA events). */
+void* m5_stream(m5_ctx* ctx);
+/* Kernel-class timing with CUDA events on the context's stream (bench.py's roofline leg).  kind 0 = tcgen05 GEMM,
+ * 1 = flash attention.  m5_profile_read returns, accumulated since the last enable: total device ms, algorithmic
+ * FLOPs (2*M*N*K per GEMM; 4*q*k*64 per attention head pair), algorithmic bytes and number of launches. */
+int m5_profile_enable(m5_ctx* ctx, int32_t on);
+int m5_profile_read(m5_ctx* ctx, int32_t kind, double* ms, double* flops, double* bytes, int64_t* launches);
 
 /* ---- AR: replaces ar_generate (mars5/ar_generate.py:15-165) for B independent utterances ------------------- */
 typedef struct {

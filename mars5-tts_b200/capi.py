@@ -50,6 +50,9 @@ _SIGS = {
     "m5_sync": (_I, [_P]),
     "m5_launch_count": (C.c_int64, [_P]),
     "m5_num_sms": (_I, [_P]),
+    "m5_stream": (_P, [_P]),
+    "m5_profile_enable": (_I, [_P, _I]),
+    "m5_profile_read": (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "m5_ar_generate": (_I, [_P, _I, _P, _P, _P, _P, _P, C.POINTER(ArCfg), _I, _P, _I, C.c_uint64, _P, _P, _P, _P, _P, _I]),
     "m5_nar_infer": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, C.POINTER(NarCfg), _I, _P, _P, C.c_uint64, _P, _P]),
     "m5_nar_forward": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),

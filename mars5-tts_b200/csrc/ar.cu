@@ -135,6 +135,7 @@ static int ar_build_plan(m5_ctx* ctx, Arena& ar, ArPlan& p, int B, const int* pr
     last.push_back(pr - 1);
   }
   p.seq.n = B; p.seq.rows = pr; p.seq.max_len = pmx;
+  for (int b = 0; b < B; ++b) { p.seq.self_pairs += (double)(1 + p.P[b]) * (1 + p.P[b]); p.spk.self_pairs += (double)(1 + p.Pf[b]) * (1 + p.Pf[b]); }
   p.spk_code_row = upload(ctx, ar, code_row); p.spk_pos = upload(ctx, ar, spos); p.spk_first = upload(ctx, ar, sfirst);
   int* d_sstart = upload(ctx, ar, sstart); int* d_slen = upload(ctx, ar, slen);
   p.spk.start = d_sstart; p.spk.len = d_slen;
@@ -196,6 +197,7 @@ static int ar_prefill_trunk(m5_ctx* ctx, const ArWeights& w, const ArPlan& p, fl
     a.Q = bs.qkv16; a.ldq = 3 * D; a.K = kcl; a.V = vcl; a.ldk = a.ldv = D; a.O = bs.att16; a.ldo = D;
     a.n_heads = c.ar_heads; a.n_seqs = p.B; a.max_q = p.seq.max_len; a.q_start = p.seq.start; a.q_len = p.seq.len;
     a.k_start = kc_start; a.k_len = p.seq.len; a.causal = 1;
+    a.flops_hint = 128.0 * c.ar_heads * p.seq.self_pairs;
     M5_TRY(run_attn(ctx, a));
     GemmCall go;
     go.A = bs.att16; go.W = lw.wo; go.M = rows; go.N = D; go.K = D; go.lda = D; go.ldw = D; go.out = x; go.ldc = D;

@@ -36,6 +36,40 @@ const m5_tensor* find_weight(m5_ctx* c, const std::string& name) {
   return &it->second;
 }
 
+static cudaEvent_t prof_get(m5_ctx* c) {
+  if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+cudaEvent_t prof_begin(m5_ctx* c) {
+  if (!c->prof_on) return nullptr;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(c->stream, &st);
+  if (st != cudaStreamCaptureStatusNone) return nullptr;
+  cudaEvent_t a = prof_get(c);
+  cudaEventRecord(a, c->stream);
+  return a;
+}
+void prof_end(m5_ctx* c, cudaEvent_t a, int kind, double flops, double bytes) {
+  if (!a) return;
+  cudaEvent_t b = prof_get(c);
+  cudaEventRecord(b, c->stream);
+  c->prof_pending.push_back({a, b, kind, flops, bytes});
+  if (c->prof_pending.size() >= 4096) { cudaStreamSynchronize(c->stream); prof_resolve(c); }
+}
+void prof_resolve(m5_ctx* c) {
+  for (auto& r : c->prof_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      c->prof_ms[r.kind] += ms; c->prof_flops[r.kind] += r.flops; c->prof_bytes[r.kind] += r.bytes; c->prof_n[r.kind] += 1;
+    }
+    c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b);
+  }
+  c->prof_pending.clear();
+  cudaGetLastError();
+}
+
 }  // namespace m5
 
 using namespace m5;
@@ -95,6 +129,25 @@ int m5_sync(m5_ctx* ctx) {
 }
 
 int64_t m5_launch_count(m5_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* m5_stream(m5_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int m5_profile_enable(m5_ctx* ctx, int32_t on) {
+  if (!ctx) return M5_ERR_ARG;
+  cudaStreamSynchronize(ctx->stream);
+  prof_resolve(ctx);
+  ctx->prof_on = on != 0;
+  for (int i = 0; i < 4; ++i) { ctx->prof_ms[i] = ctx->prof_flops[i] = ctx->prof_bytes[i] = 0; ctx->prof_n[i] = 0; }
+  return M5_OK;
+}
+int m5_profile_read(m5_ctx* ctx, int32_t kind, double* ms, double* flops, double* bytes, int64_t* launches) {
+  if (!ctx || kind < 0 || kind >= 4) return M5_ERR_ARG;
+  cudaStreamSynchronize(ctx->stream);
+  prof_resolve(ctx);
+  if (ms) *ms = ctx->prof_ms[kind];
+  if (flops) *flops = ctx->prof_flops[kind];
+  if (bytes) *bytes = ctx->prof_bytes[kind];
+  if (launches) *launches = ctx->prof_n[kind];
+  return M5_OK;
+}
 int m5_num_sms(m5_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
 
 // ------------------------------------------------------------------------------------------------ debug entry points

@@ -15,6 +15,14 @@ struct m5_ctx {
   std::string last_error;
   int64_t launches = 0;
 
+  // optional kernel-class profiling (bench.py roofline leg): event pairs resolved at the end of a public call
+  struct ProfRec { cudaEvent_t a, b; int kind; double flops, bytes; };
+  bool prof_on = false;
+  std::vector<ProfRec> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[4] = {0, 0, 0, 0}, prof_flops[4] = {0, 0, 0, 0}, prof_bytes[4] = {0, 0, 0, 0};
+  int64_t prof_n[4] = {0, 0, 0, 0};
+
   // grow-only device arena, reset at the start of every public call
   char* arena = nullptr;
   size_t arena_cap = 0, arena_off = 0;
@@ -53,6 +61,10 @@ struct Arena {
 };
 
 const m5_tensor* find_weight(m5_ctx* c, const std::string& name);
+// profiling helpers: bracket one launch with events when profiling is on
+cudaEvent_t prof_begin(m5_ctx* c);
+void prof_end(m5_ctx* c, cudaEvent_t a, int kind, double flops, double bytes);
+void prof_resolve(m5_ctx* c);  // call after a stream synchronize
 template <typename T>
 inline const T* W(m5_ctx* c, const std::string& name) {
   const m5_tensor* t = find_weight(c, name);

@@ -139,14 +139,14 @@ int gemm_skinny(const SkinnyCall& c, cudaStream_t stream, int num_sms) {
   const int NT = c.B <= 8 ? 1 : (c.B <= 16 ? 2 : 4);
   const size_t smem = (size_t)(8 * NT) * (kblk * 2 + 64) + (size_t)SK_WARPS * SK_ROWS * 8 * NT * sizeof(float);
   const int grid = (c.N + SK_ROWS - 1) / SK_ROWS;
-  auto launch = [&](auto kern) {
-    static bool set = false;
-    if (!set) {
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      set = true;
-    }
-    kern<<<grid, SK_THREADS, smem, stream>>>(c, kblk, n_kblk);
-  };
+  static bool attr_set = false;
+  if (!attr_set) {  // opt in to > 48 KB dynamic shared memory once for every instantiation
+    cudaFuncSetAttribute(gemm_skinny_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gemm_skinny_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gemm_skinny_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  auto launch = [&](auto kern) { kern<<<grid, SK_THREADS, smem, stream>>>(c, kblk, n_kblk); };
   if (NT == 1) launch(gemm_skinny_kernel<1>);
   else if (NT == 2) launch(gemm_skinny_kernel<2>);
   else launch(gemm_skinny_kernel<4>);

@@ -3,7 +3,13 @@
 namespace m5 {
 
 int run_gemm(m5_ctx* ctx, const GemmCall& g) {
+  cudaEvent_t pe = prof_begin(ctx);
   int r = gemm_tc5(g, ctx->stream, ctx->num_sms);
+  if (pe) {
+    const double out_b = (g.mode == M5_OUT_F32) ? 4.0 * (g.accumulate ? 2 : 1) : 2.0;
+    const double wk = g.kwrap > 0 ? g.kwrap : g.K, ak = g.awrap > 0 ? g.awrap : g.K;
+    prof_end(ctx, pe, 0, 2.0 * g.M * (double)g.N * g.K, 2.0 * g.M * ak + 2.0 * g.N * wk + out_b * g.M * (double)g.N);
+  }
   if (r != M5_OK) return ctx->fail(r, "gemm_tc5 failed (M=" + std::to_string(g.M) + " N=" + std::to_string(g.N) + " K=" +
                                           std::to_string(g.K) + "): " + cudaGetErrorString(cudaGetLastError()));
   ctx->launches += 1;
@@ -16,7 +22,9 @@ int run_norm(m5_ctx* ctx, const NormCall& n) {
   return M5_OK;
 }
 int run_attn(m5_ctx* ctx, const AttnCall& a) {
+  cudaEvent_t pe = prof_begin(ctx);
   int r = flash_attn(a, ctx->stream);
+  if (pe) prof_end(ctx, pe, 1, a.flops_hint, 0.0);
   if (r != M5_OK) return ctx->fail(r, "flash_attn failed");
   ctx->launches += 1;
   return M5_OK;
@@ -102,6 +110,7 @@ int encoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const EncLayerW& w,
   a.Q = s.qkv16; a.K = s.qkv16 + D; a.V = s.qkv16 + 2 * D; a.ldq = a.ldk = a.ldv = 3 * D;
   a.O = s.att16; a.ldo = D; a.n_heads = H; a.n_seqs = seqs.n; a.max_q = seqs.max_len;
   a.q_start = seqs.start; a.q_len = seqs.len; a.k_start = seqs.start; a.k_len = seqs.klen ? seqs.klen : seqs.len;
+  a.flops_hint = 256.0 * H * seqs.self_pairs;
   M5_TRY(run_attn(ctx, a));
   GemmCall go = lin(s.att16, rows, D, false, w.out_w, D, w.out_b);
   go.out = x; go.ldc = D; go.mode = M5_OUT_F32; go.accumulate = 1;
@@ -122,6 +131,7 @@ int decoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const __half* mem16
   a.Q = s.qkv16; a.K = s.qkv16 + D; a.V = s.qkv16 + 2 * D; a.ldq = a.ldk = a.ldv = 3 * D;
   a.O = s.att16; a.ldo = D; a.n_heads = H; a.n_seqs = seqs.n; a.max_q = seqs.max_len;
   a.q_start = seqs.start; a.q_len = seqs.len; a.k_start = seqs.start; a.k_len = seqs.len;
+  a.flops_hint = 256.0 * H * seqs.self_pairs;
   M5_TRY(run_attn(ctx, a));
   GemmCall go = lin(s.att16, rows, D, false, w.sa_out_w, D, w.sa_out_b);
   go.out = x; go.ldc = D; go.mode = M5_OUT_F32; go.accumulate = 1;
@@ -138,6 +148,7 @@ int decoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const __half* mem16
   c.Q = s.qkv16; c.ldq = D; c.K = s.kv16; c.V = s.kv16 + D; c.ldk = c.ldv = 2 * D;
   c.O = s.att16; c.ldo = D; c.n_heads = H; c.n_seqs = seqs.n; c.max_q = seqs.max_len;
   c.q_start = seqs.start; c.q_len = seqs.len; c.k_start = mem_seqs.start; c.k_len = mem_seqs.len;
+  c.flops_hint = 256.0 * H * seqs.cross_pairs;
   M5_TRY(run_attn(ctx, c));
   GemmCall gco = lin(s.att16, rows, D, false, w.ca_out_w, D, w.ca_out_b);
   gco.out = x; gco.ldc = D; gco.mode = M5_OUT_F32; gco.accumulate = 1;

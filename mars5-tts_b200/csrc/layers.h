@@ -17,6 +17,8 @@ struct SeqSet {
   const int* start = nullptr;  // device [n]
   const int* len = nullptr;    // device [n]
   const int* klen = nullptr;   // device [n] optional: visible keys per sequence (key-padding mask), default = len
+  double self_pairs = 0;       // sum_s len_s^2 (profiling: attention FLOPs)
+  double cross_pairs = 0;      // sum_s len_s * mem_len_s (decoder sets only)
 };
 
 struct EncLayerW {

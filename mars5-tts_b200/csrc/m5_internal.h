@@ -73,6 +73,7 @@ struct AttnCall {
   const int* k_start = nullptr; const int* k_len = nullptr;
   int causal = 0;  // key j visible to query i iff j <= i + (k_len - q_len)
   float scale = 0.125f;
+  double flops_hint = 0.0;  // 4 * 64 * heads * sum_s(q_len*k_len) (halved when causal); profiling only
 };
 int flash_attn(const AttnCall& c, cudaStream_t stream);
 

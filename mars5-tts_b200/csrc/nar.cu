@@ -112,6 +112,7 @@ static int build_plan(m5_ctx* ctx, Arena& ar, NarPlan& p, int B, const int* c_te
   }
   start.push_back(r); len.push_back(1); first.push_back(r); code_row.push_back(-1); pos.push_back(0); r += 1;
   p.spk.n = B + 1; p.spk.rows = r; p.spk.max_len = mx;
+  for (int v : len) p.spk.self_pairs += (double)v * v;
   p.spk_code_row = upload(ctx, ar, code_row); p.spk_pos = upload(ctx, ar, pos);
   p.spk_start = upload(ctx, ar, start); p.spk_len = upload(ctx, ar, len); p.spk_first = upload(ctx, ar, first);
   p.spk.start = p.spk_start; p.spk.len = p.spk_len;
@@ -144,6 +145,11 @@ static int build_plan(m5_ctx* ctx, Arena& ar, NarPlan& p, int B, const int* c_te
   }
   p.enc.n = npass * B; p.enc.rows = er; p.enc.max_len = emx;
   p.dec.n = npass * B; p.dec.rows = dr; p.dec.max_len = dmx;
+  for (size_t i = 0; i < elen.size(); ++i) {
+    p.enc.self_pairs += (double)elen[i] * elen[i];
+    p.dec.self_pairs += (double)dlen[i] * dlen[i];
+    p.dec.cross_pairs += (double)dlen[i] * elen[i];
+  }
   p.enc_tok = upload(ctx, ar, etok); p.enc_pos = upload(ctx, ar, epos);
   p.enc_start = upload(ctx, ar, estart); p.enc_len = upload(ctx, ar, elen);
   p.dec_xrow = upload(ctx, ar, dx); p.dec_pos = upload(ctx, ar, dpos);

@@ -53,10 +53,18 @@ M5_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+M5_DEVINL uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Watchdog: a protocol bug must trap within ~2 s of wall time instead of hanging the GPU box.
 M5_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > M5_SPIN_LIMIT) {
+    if ((++spins & 0xFF) == 0 && global_timer_ns() - t0 > 2000000000ull) {
       printf("m5: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }
