@@ -102,6 +102,17 @@ class Engine:
     def launches(self):
         return int(self.lib.m5_launch_count(self.ctx))
 
+    # ------------------------------------------------------------------------------------------ helpers
+    @staticmethod
+    def _mem(x):
+        return capi.MEM_DEVICE if torch.is_tensor(x) and x.is_cuda else capi.MEM_HOST
+
+    def _alloc(self, mem, shape, dtype):
+        if mem == capi.MEM_DEVICE:
+            return torch.zeros(shape, dtype={np.int32: torch.int32, np.float32: torch.float32}[dtype],
+                               device=torch.device("cuda", self.device))
+        return np.zeros(shape, dtype=dtype)
+
     # ------------------------------------------------------------------------------------------ AR
     def make_ar_cfg(self, icfg: InferenceConfig, max_len, eos_id, force_len=0, sync_every=16):
         c = capi.ArCfg()
@@ -111,28 +122,34 @@ class Engine:
         c.max_len, c.eos_id, c.force_len, c.sync_every = max_len, eos_id, force_len, sync_every
         return c
 
-    def ar_generate(self, prompts, spk_codes, n_phones, ar_cfg, noise=None, seed=0, utt_ids=None, dump_steps=0):
-        """prompts: list of int sequences; spk_codes: list of (Pf, 8) arrays.  Host buffers (mem = HOST).
-        Returns (list of id arrays, hit_maxlen list, logits dump or None)."""
-        B = len(prompts)
-        ids, plen = _cat_i32(prompts), _i32([len(p) for p in prompts])
-        codes, slen = _cat_i32(spk_codes, 8), _i32([len(s) for s in spk_codes])
-        nph = _i32(n_phones) if n_phones is not None else None
+    def ar_generate_packed(self, ids, plen, codes, slen, nph, ar_cfg, noise=None, seed=0, utt=None, dump_steps=0):
+        """Packed form: `ids` [sum plen] and `codes` [sum slen, 8] are int32 numpy arrays (HOST) or CUDA tensors (DEVICE);
+        plen / slen / nph / utt are host arrays.  Returns (out_ids [B, max_len], out_len, hit, dump) in the same memory."""
+        mem, B = self._mem(ids), len(plen)
+        # keep every temporary alive until the C call returns (ctypes only sees raw addresses)
+        plen_a, slen_a = _i32(plen), _i32(slen)
+        nph_a = _i32(nph) if nph is not None else None
+        utt_a = np.ascontiguousarray(np.asarray(utt, dtype=np.int64)) if utt is not None else None
         V, max_len = self.dims["ar_vocab"], ar_cfg.max_len
-        out_ids = np.zeros((B, max_len), dtype=np.int32)
+        out_ids = self._alloc(mem, (B, max_len), np.int32)
         out_len, hit = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
-        noise_np, nsteps = None, 0
-        if noise is not None:
-            noise_np = np.ascontiguousarray(np.asarray(noise, dtype=np.float32))
-            nsteps = noise_np.shape[1]
-        dump = np.zeros((B, dump_steps, V), dtype=np.float32) if dump_steps else None
-        utt = np.ascontiguousarray(np.asarray(utt_ids, dtype=np.int64)) if utt_ids is not None else None
-        rc = self.lib.m5_ar_generate(self.ctx, B, capi.ptr(ids), capi.ptr(plen), capi.ptr(codes), capi.ptr(slen),
-                                     capi.ptr(nph), C.byref(ar_cfg), capi.MEM_HOST, capi.ptr(noise_np), nsteps,
-                                     C.c_uint64(seed), capi.ptr(utt), capi.ptr(out_ids), capi.ptr(out_len), capi.ptr(hit),
-                                     capi.ptr(dump), dump_steps)
+        nsteps = 0 if noise is None else noise.shape[1]
+        dump = self._alloc(mem, (B, dump_steps, V), np.float32) if dump_steps else None
+        rc = self.lib.m5_ar_generate(self.ctx, B, capi.ptr(ids), capi.ptr(plen_a), capi.ptr(codes), capi.ptr(slen_a),
+                                     capi.ptr(nph_a), C.byref(ar_cfg), mem, capi.ptr(noise), nsteps, C.c_uint64(seed),
+                                     capi.ptr(utt_a), capi.ptr(out_ids), capi.ptr(out_len), capi.ptr(hit), capi.ptr(dump),
+                                     dump_steps)
         capi.check(self.ctx, rc, "m5_ar_generate")
-        return [out_ids[b, :out_len[b]].copy() for b in range(B)], hit.tolist(), dump
+        return out_ids, out_len, hit, dump
+
+    def ar_generate(self, prompts, spk_codes, n_phones, ar_cfg, noise=None, seed=0, utt_ids=None, dump_steps=0):
+        """prompts: list of int sequences; spk_codes: list of (Pf, 8) arrays (host buffers).
+        Returns (list of id arrays, hit_maxlen list, logits dump or None)."""
+        nz = np.ascontiguousarray(np.asarray(noise, dtype=np.float32)) if noise is not None else None
+        out_ids, out_len, hit, dump = self.ar_generate_packed(_cat_i32(prompts), [len(p) for p in prompts], _cat_i32(spk_codes, 8),
+                                                              [len(s) for s in spk_codes], n_phones, ar_cfg, nz, seed, utt_ids,
+                                                              dump_steps)
+        return [out_ids[b, :out_len[b]].copy() for b in range(len(prompts))], hit.tolist(), dump
 
     def ar_forward(self, prompts, spk_codes):
         B = len(prompts)
@@ -159,21 +176,26 @@ class Engine:
         c.schedule = self.schedule(T).ctypes.data
         return c
 
+    def nar_infer_packed(self, text, tlen, codes, clen, l0, xlen, nar_cfg, x_init=None, noise=None, seed=0, utt=None):
+        """Packed form (numpy = HOST, CUDA tensors = DEVICE).  Returns codes [sum xlen, 8] in the same memory."""
+        mem, B = self._mem(text), len(tlen)
+        tlen_a, clen_a, xlen_a = _i32(tlen), _i32(clen), _i32(xlen)
+        utt_a = np.ascontiguousarray(np.asarray(utt, dtype=np.int64)) if utt is not None else None
+        out = self._alloc(mem, (int(np.sum(xlen)), 8), np.int32)
+        rc = self.lib.m5_nar_infer(self.ctx, B, capi.ptr(text), capi.ptr(tlen_a), capi.ptr(codes), capi.ptr(clen_a),
+                                   capi.ptr(l0), capi.ptr(xlen_a), C.byref(nar_cfg), mem, capi.ptr(x_init), capi.ptr(noise),
+                                   C.c_uint64(seed), capi.ptr(utt_a), capi.ptr(out))
+        capi.check(self.ctx, rc, "m5_nar_infer")
+        return out
+
     def nar_infer(self, c_text, c_codes, x_l0, nar_cfg, x_init=None, noise=None, seed=0, utt_ids=None):
-        B = len(c_text)
-        text, tlen = _cat_i32(c_text), _i32([len(t) for t in c_text])
-        codes, clen = _cat_i32(c_codes, 8), _i32([len(c) for c in c_codes])
-        l0, xlen = _cat_i32(x_l0), _i32([len(x) for x in x_l0])
+        xlen = [len(x) for x in x_l0]
         xi = _cat_i32(x_init, 8) if x_init is not None else None
         nz = np.ascontiguousarray(np.asarray(noise, dtype=np.float32)) if noise is not None else None
-        utt = np.ascontiguousarray(np.asarray(utt_ids, dtype=np.int64)) if utt_ids is not None else None
-        out = np.zeros((int(xlen.sum()), 8), dtype=np.int32)
-        rc = self.lib.m5_nar_infer(self.ctx, B, capi.ptr(text), capi.ptr(tlen), capi.ptr(codes), capi.ptr(clen),
-                                   capi.ptr(l0), capi.ptr(xlen), C.byref(nar_cfg), capi.MEM_HOST, capi.ptr(xi),
-                                   capi.ptr(nz), C.c_uint64(seed), capi.ptr(utt), capi.ptr(out))
-        capi.check(self.ctx, rc, "m5_nar_infer")
+        out = self.nar_infer_packed(_cat_i32(c_text), [len(t) for t in c_text], _cat_i32(c_codes, 8), [len(c) for c in c_codes],
+                                    _cat_i32(x_l0), xlen, nar_cfg, xi, nz, seed, utt_ids)
         offs = np.concatenate([[0], np.cumsum(xlen)])
-        return [out[offs[b]:offs[b + 1]] for b in range(B)]
+        return [out[offs[b]:offs[b + 1]] for b in range(len(c_text))]
 
     def nar_forward(self, c_text, c_codes, x, t, drop_cond=False, precise=False):
         B = len(c_text)
@@ -190,15 +212,18 @@ class Engine:
         return [out[offs[b]:offs[b + 1]] for b in range(B)]
 
     # ------------------------------------------------------------------------------------------ vocoder
-    def vocode(self, codes, bandwidth_id=1):
-        B = len(codes)
-        cs, nf = _cat_i32(codes, 8), _i32([len(c) for c in codes])
-        hop = self.dims["voc_hop"]
-        out = np.zeros(int(nf.sum()) * hop, dtype=np.float32)
-        rc = self.lib.m5_vocode(self.ctx, B, capi.ptr(cs), capi.ptr(nf), int(bandwidth_id), capi.MEM_HOST, capi.ptr(out))
+    def vocode_packed(self, codes, n_frames, bandwidth_id=1):
+        mem, nf_a = self._mem(codes), _i32(n_frames)
+        out = self._alloc(mem, (int(np.sum(n_frames)) * self.dims["voc_hop"],), np.float32)
+        rc = self.lib.m5_vocode(self.ctx, len(n_frames), capi.ptr(codes), capi.ptr(nf_a), int(bandwidth_id), mem, capi.ptr(out))
         capi.check(self.ctx, rc, "m5_vocode")
-        offs = np.concatenate([[0], np.cumsum(nf)]) * hop
-        return [out[offs[b]:offs[b + 1]] for b in range(B)]
+        return out
+
+    def vocode(self, codes, bandwidth_id=1):
+        nf = [len(c) for c in codes]
+        out = self.vocode_packed(_cat_i32(codes, 8), nf, bandwidth_id)
+        offs = np.concatenate([[0], np.cumsum(nf)]) * self.dims["voc_hop"]
+        return [out[offs[b]:offs[b + 1]] for b in range(len(codes))]
 
 
 class Mars5TTS:

@@ -11,7 +11,7 @@ FULL = dict(ar_dim=1536, ar_layers=26, ar_spk_layers=2, nar_dim=1024, nar_enc_la
             nar_spk_layers=3, n_text=2048, n_speech=5952, voc_feat=128, voc_dim=384, voc_inter=1152, voc_layers=8)
 TINY = dict(ar_dim=192, ar_layers=2, ar_spk_layers=1, nar_dim=128, nar_enc_layers=1, nar_dec_layers=2,
             nar_spk_layers=1, n_text=258, n_speech=1025, voc_feat=64, voc_dim=128, voc_inter=256, voc_layers=2)
-MID = dict(ar_dim=512, ar_layers=4, ar_spk_layers=2, nar_dim=512, nar_enc_layers=2, nar_dec_layers=4,
+MID = dict(ar_dim=768, ar_layers=4, ar_spk_layers=2, nar_dim=512, nar_enc_layers=2, nar_dec_layers=4,
            nar_spk_layers=2, n_text=258, n_speech=1025, voc_feat=128, voc_dim=384, voc_inter=1152, voc_layers=3)
 
 

@@ -187,3 +187,44 @@ def ar_generate(sd, cfg, prompt, spk_codes, scfg, noise, max_len, n_phones_gen, 
         hit = True
     out = (torch.tensor(ids), hit)
     return out + (torch.stack(all_logits),) if return_logits else out
+
+
+# ------------------------------------------------------------------------------------------------ KV-cached stepping
+class KVCache:
+    """Per-layer K/V of everything fed so far (RotatingBufferCache without the wrap, nn_future.py:89-134)."""
+
+    def __init__(self):
+        self.k, self.v, self.n = {}, {}, 0
+
+
+def codeclm_step(sd, cfg, new_ids, spk_codes, cache):
+    """One CodecLM.forward call of the reference's cached loop (ar_generate.py:62-71, model.py:95-141): the speaker
+    vector is recomputed on EVERY call exactly like the reference does; on the first call (empty cache) the whole prompt
+    plus the speaker slot is processed, afterwards only the newest token.  Returns logits of the last position."""
+    nhead, n_layers, eps = cfg["ar_heads"], cfg["ar_layers"], 1e-5
+    spk = speaker_vector(sd, spk_codes, nhead, cfg["ar_spk_layers"], "ref_chunked_emb", "pos_embedding.alpha",
+                         key_len=ar_spk_key_len(spk_codes))
+    x = sd["embed.weight"][new_ids]
+    if cache.n == 0:
+        h = torch.cat([spk[None], x], dim=0)
+    else:
+        h = x[-1:]
+    L, D = h.shape
+    pos = torch.arange(cache.n, cache.n + L)
+    for l in range(n_layers):
+        p = f"ar.layers.{l}."
+        xn = rmsnorm(h, sd[p + "attention_norm.weight"], eps)
+        q = rope((xn @ sd[p + "attention.wq.weight"].T).view(L, nhead, 64), pos)
+        k = rope((xn @ sd[p + "attention.wk.weight"].T).view(L, nhead, 64), pos)
+        v = (xn @ sd[p + "attention.wv.weight"].T).view(L, nhead, 64)
+        cache.k[l] = k if cache.n == 0 else torch.cat([cache.k[l], k], dim=0)
+        cache.v[l] = v if cache.n == 0 else torch.cat([cache.v[l], v], dim=0)
+        s = torch.einsum("qhd,khd->hqk", q, cache.k[l]) / 8.0
+        if L > 1:
+            s = s + torch.log(torch.tril(torch.ones(L, L)))
+        o = torch.einsum("hqk,khd->qhd", s.softmax(-1), cache.v[l]).reshape(L, D)
+        h = h + o @ sd[p + "attention.wo.weight"].T
+        xn = rmsnorm(h, sd[p + "ffn_norm.weight"], eps)
+        h = h + (F.silu(xn @ sd[p + "feed_forward.w1.weight"].T) * (xn @ sd[p + "feed_forward.w3.weight"].T)) @ sd[p + "feed_forward.w2.weight"].T
+    cache.n += L
+    return rmsnorm(h[-1], sd["ar.norm.weight"], eps) @ sd["ar.output.weight"].T
