@@ -71,20 +71,29 @@ def to_device(wl, dev):
                 slen=[len(s) for s in wl["spk"]], text=cat(wl["text"]), tlen=[len(t) for t in wl["text"]])
 
 
+PHASE_S = {"ar": 0.0, "nar": 0.0, "voc": 0.0}
+
+
 def run_step_device(eng, icfg, wl, dw, T, precise, seed=0):
     """Same step with every data buffer resident on the device (mem = M5_MEM_DEVICE); the glue is slicing on device."""
     B, N, Pf, fci = wl["B"], wl["N"], wl["Pf"], wl["first_codec_idx"]
+    t0 = time.perf_counter()
     eos = eng.dims["ar_vocab"] - 1
     acfg = eng.make_ar_cfg(icfg, wl["max_len"], eos, force_len=N, sync_every=64)
     out_ids, out_len, _, _ = eng.ar_generate_packed(dw["ids"], dw["plen"], dw["codes"], dw["slen"], wl["n_phones"], acfg,
                                                     seed=seed, utt=wl["utt"])
     L = int(out_len[0])  # forced length: identical for every row
+    t1 = time.perf_counter()
     l0 = ((out_ids[:, fci:L] - wl["n_text"]).clamp_(min=0) % 1024).to(torch.int32).reshape(-1).contiguous()
     xlen = [L - fci] * B
     ncfg = eng.make_nar_cfg(icfg, T=T, precise=precise)
     codes = eng.nar_infer_packed(dw["text"], dw["tlen"], dw["codes"], dw["slen"], l0, xlen, ncfg, seed=seed, utt=wl["utt"])
+    t2 = time.perf_counter()
     outs = codes.view(B, L - fci, 8)[:, Pf:].contiguous().view(-1, 8)
-    return eng.vocode_packed(outs, [L - fci - Pf] * B, bandwidth_id=1)
+    wav = eng.vocode_packed(outs, [L - fci - Pf] * B, bandwidth_id=1)
+    t3 = time.perf_counter()  # every C-ABI call returns after its stream has drained: host timers bracket device work
+    PHASE_S["ar"] += t1 - t0; PHASE_S["nar"] += t2 - t1; PHASE_S["voc"] += t3 - t2
+    return wav
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -267,6 +276,8 @@ def main():
     if rank == 0:
         sampler.start()
     eng.lib.m5_profile_enable(eng.ctx, 1)
+    for k in PHASE_S:
+        PHASE_S[k] = 0.0
     l0 = eng.launches
     ms, wav_dev = timed(args.steps, step_dev)
     launches = eng.launches - l0
@@ -278,6 +289,7 @@ def main():
         prof[name] = dict(ms=a.value, flops=b.value, bytes=c.value, launches=n.value)
     eng.lib.m5_profile_enable(eng.ctx, 0)
     clocks = sampler.stop() if rank == 0 else {}
+    phases = {k: round(v / args.steps * 1e3, 1) for k, v in PHASE_S.items()}
     ms_e2e, wavs = (ms, None) if args.no_e2e else timed(args.steps, step_host)
     audio_total = wl["audio_s"] * world * args.steps
     value = audio_total / (ms / 1e3)
@@ -300,7 +312,7 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f16 operands / f32 accumulate", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
-           "gpu_launches": int(launches), "roofline": roofline, "realtime_factor_per_gpu": value / world}
+           "gpu_launches": int(launches), "roofline": roofline, "phase_ms_per_step": phases, "realtime_factor_per_gpu": value / world}
     if world == 1 and not args.no_cpu_baseline:
         v, detail = cpu_port_sample(size, make_workload(size, 1, 1234, **wl_kw), args.T)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",

@@ -3,15 +3,19 @@
 //   * A (activations) and W (weights, nn.Linear layout [out,in]) are fp16, K-major; accumulation is fp32 in TMEM.
 //   * warp 0      : TMA producer  (cp.async.bulk.tensor 2-D, 128B swizzle, mbarrier complete_tx)
 //     warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16)
-//     warps 2..5  : epilogue (tcgen05.ld 32x32b.x32 -> registers -> fused bias/activation/gate/residual -> global)
+//     warps 2..5  : epilogue: tcgen05.ld 32x32b.x32 (lane = accumulator row) -> padded smem tile -> registers with
+//                   lane = 4 consecutive columns, so every global access is a whole 128-byte row segment; bias / column
+//                   scale of the tile are staged in smem while the MMAs of the tile are still running; the TMEM load of
+//                   chunk c+1 is in flight while chunk c is stored; residual rows are prefetched before the adds.
 //   * 2 accumulator stages in TMEM (2*BLOCK_N columns) so the epilogue of tile i overlaps the main loop of tile i+1.
 //   * Tile order keeps a band of 148 M-tiles (<= 39 MB of A at K=1024) L2-resident while sweeping N.
+//   * The epilogue is compiled per output kind (template) to keep the instruction footprint inside the I-cache.
 //
 // This one kernel serves every dense contraction of the hot path whose M is large: the NAR encoder/decoder/speaker
 // projections (reference: nn.MultiheadAttention in/out-proj, FNNSwiGLU nn_future.py:13-29, linear2, the 8 output heads
 // model.py:234-240), the AR prefill projections (nn_future.py:241,274,297-298,398) and the Vocos pointwise convs.
-// "split" mode (kwrap > 0): A holds [hi | lo] fp16 halves of an fp32 activation (K = 2*kwrap) and the W tile is
-// re-read for the second half, giving fp32-class accuracy at 2x the tensor work.
+// "split" operands: kwrap > 0 -> A = [hi | lo] fp16 halves of an fp32 activation (K = 2*kwrap), W re-read modulo kwrap;
+// awrap > 0 -> A re-read modulo awrap against W = [W_hi | W_hi | W_lo]: fp32-class accuracy at 2-3x the tensor work.
 #include <cuda.h>
 #include <stdio.h>
 
@@ -26,6 +30,9 @@ static constexpr int UMMA_K = 16;
 static constexpr int GEMM_THREADS = 192;
 static constexpr int M_BAND = 148;  // M-tiles kept L2-resident per sweep over N
 
+// epilogue kinds (compile-time)
+enum { E_F32 = 0, E_F32_ACC = 1, E_F16 = 2, E_SWIGLU = 3, E_GENERIC = 4 };
+
 template <int BLOCK_N>
 struct GemmSmem {
   static constexpr int STAGES = (BLOCK_N == 256) ? 4 : ((BLOCK_N == 128) ? 6 : 8);
@@ -33,34 +40,115 @@ struct GemmSmem {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + alignment slack
+  static constexpr int EPI_OFF = BAR_OFF + 256;             // 4 epilogue warps x [32 rows][36 floats] transpose tiles
+  static constexpr int EPI_BYTES = 4 * 32 * 36 * 4;
+  static constexpr int BIAS_OFF = EPI_OFF + EPI_BYTES;      // per epilogue warp: bias[BLOCK_N] | colscale[BLOCK_N]
+  static constexpr int BIAS_BYTES = 4 * 2 * BLOCK_N * 4;
+  static constexpr int TOTAL = BIAS_OFF + BIAS_BYTES + 1024;  // + alignment slack
 };
 
 struct GemmEpi {
   const float* bias;      // [N] fp32 or null
   const float* colscale;  // [N] fp32 or null (Vocos layer-scale gamma)
   void* out;              // fp32 or fp16, row stride ldc (elements)
-  void* out_lo;           // M5_OUT_F16_SPLIT: low halves
+  void* out_lo;           // split modes: low halves
   int ldc;
   int mode;        // M5_OUT_*
   int act;         // M5_ACT_*
   int accumulate;  // fp32 out: out += value (residual stream update)
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == M5_ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
-  if (act == M5_ACT_SILU) return v / (1.0f + __expf(-v));
-  return v;
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+__device__ __forceinline__ float silu_f(float a) { return a / (1.0f + __expf(-a)); }
+
+// Stores 4 consecutive columns [col, col+4) of one row. v already holds accumulator + bias.
+template <int KIND>
+__device__ __forceinline__ void epi_store4(const GemmEpi& epi, float (&v)[4], const float (&s4)[4], const float4& prev, int row,
+                                           int col, int N, bool full4) {
+  if constexpr (KIND == E_F32 || KIND == E_F32_ACC) {
+    float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldc + col;
+    if constexpr (KIND == E_F32_ACC) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] *= s4[e];
+    }
+    if (full4) {
+      float4 w = make_float4(v[0], v[1], v[2], v[3]);
+      if constexpr (KIND == E_F32_ACC) { w.x += prev.x; w.y += prev.y; w.z += prev.z; w.w += prev.w; }
+      *reinterpret_cast<float4*>(o) = w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (col + e < N) o[e] = (KIND == E_F32_ACC) ? o[e] + v[e] : v[e];
+    }
+  } else if constexpr (KIND == E_F16) {
+    __half* o = reinterpret_cast<__half*>(epi.out) + (size_t)row * epi.ldc + col;
+    const __half h0 = __float2half_rn(v[0]), h1 = __float2half_rn(v[1]), h2 = __float2half_rn(v[2]), h3 = __float2half_rn(v[3]);
+    if (full4) {
+      *reinterpret_cast<uint2*>(o) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+    } else {
+      if (col + 0 < N) o[0] = h0;
+      if (col + 1 < N) o[1] = h1;
+      if (col + 2 < N) o[2] = h2;
+    }
+  } else if constexpr (KIND == E_SWIGLU) {
+    // columns (2j, 2j+1) = (W_j x, V_j x) -> silu(W x) * V x ; N is even
+    __half* o = reinterpret_cast<__half*>(epi.out) + (size_t)row * epi.ldc + (col >> 1);
+    const __half h0 = __float2half_rn(silu_f(v[0]) * v[1]), h1 = __float2half_rn(silu_f(v[2]) * v[3]);
+    if (full4) *reinterpret_cast<uint32_t*>(o) = pack_h2(h0, h1);
+    else if (col + 1 < N) o[0] = h0;
+  } else {  // E_GENERIC: activations, column scale, split (hi | lo) outputs -- cold paths (vocoder, timestep MLPs, precise mode)
+    if (epi.act == M5_ACT_GELU) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = 0.5f * v[e] * (1.0f + erff(v[e] * 0.70710678118654752440f));
+    } else if (epi.act == M5_ACT_SILU) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = silu_f(v[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] *= s4[e];
+    if (epi.mode == M5_OUT_F32) {
+      float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldc + col;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (col + e < N) o[e] = epi.accumulate ? o[e] + v[e] : v[e];
+    } else if (epi.mode == M5_OUT_F16 || epi.mode == M5_OUT_F16_SPLIT) {
+      __half* o = reinterpret_cast<__half*>(epi.out) + (size_t)row * epi.ldc + col;
+      __half* ol = reinterpret_cast<__half*>(epi.out_lo) + (size_t)row * epi.ldc + col;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (col + e < N) {
+          const __half h = __float2half_rn(v[e]);
+          o[e] = h;
+          if (epi.mode == M5_OUT_F16_SPLIT) ol[e] = __float2half_rn(v[e] - __half2float(h));
+        }
+      }
+    } else {  // SwiGLU (optionally split)
+      __half* o = reinterpret_cast<__half*>(epi.out) + (size_t)row * epi.ldc + (col >> 1);
+      __half* ol = reinterpret_cast<__half*>(epi.out_lo) + (size_t)row * epi.ldc + (col >> 1);
+      const float g[2] = {silu_f(v[0]) * v[1], silu_f(v[2]) * v[3]};
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (col + 2 * e + 1 < N) {
+          const __half h = __float2half_rn(g[e]);
+          o[e] = h;
+          if (epi.mode == M5_OUT_SWIGLU_F16_SPLIT) ol[e] = __float2half_rn(g[e] - __half2float(h));
+        }
+      }
+    }
+  }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int KIND>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N,
                 int K, int kwrap, int awrap, GemmEpi epi) {
   using S = GemmSmem<BLOCK_N>;
   constexpr int STAGES = S::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the 128B-swizzle tiles; pointer arithmetic on the __shared__ array keeps the address space
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
@@ -156,109 +244,69 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   } else {
     // ------------------------------------------------------------ epilogue warps 2..5
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    float* stg = reinterpret_cast<float*>(smem + S::EPI_OFF) + (warp - 2) * (32 * 36);
+    float* sbias = reinterpret_cast<float*>(smem + S::BIAS_OFF) + (warp - 2) * (2 * BLOCK_N);
+    float* sscale = sbias + BLOCK_N;
+    const int c4 = (lane & 7) * 4, rsub = lane >> 3;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       int m_blk, n_blk;
       tile_coords(t, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      // stage this tile's bias / column scale while the MMAs of the tile are still running
+      __syncwarp();
+      for (int j = lane; j < BLOCK_N; j += 32) {
+        const int col = n_blk * BLOCK_N + j;
+        sbias[j] = (epi.bias && col < N) ? __ldg(epi.bias + col) : 0.f;
+        if constexpr (KIND == E_F32_ACC || KIND == E_GENERIC)
+          sscale[j] = (epi.colscale && col < N) ? __ldg(epi.colscale + col) : 1.f;
+      }
+      __syncwarp();
       mbar_wait(&tmem_full[acc], acc_phase);
       tc5_fence_after();
-      const int row = m_blk * BLOCK_M + quad * 32 + lane;
-      const bool row_ok = row < M;
+      const int row_base = m_blk * BLOCK_M + quad * 32;
       const uint32_t taddr0 = tmem_base + acc * BLOCK_N + ((uint32_t)(quad * 32) << 16);
+      const int n_chunks = min(BLOCK_N / 32, (N - n_blk * BLOCK_N + 31) / 32);
+      uint32_t r[32];
+      tc5_ld_32x32(taddr0, r);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        const int col0 = n_blk * BLOCK_N + c * 32;
-        if (col0 >= N) break;  // warp-uniform
-        __syncwarp();          // reconverge before the warp-collective TMEM load
-        uint32_t r[32];
-        tc5_ld_32x32(taddr0 + c * 32, r);
+      for (int c = 0; c < n_chunks; ++c) {
+        const int col = n_blk * BLOCK_N + c * 32 + c4;  // first of this lane's 4 columns
+        const bool full4 = col + 3 < N;
         tc5_wait_ld();
-        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]);
-          const int col = col0 + j;
-          if (col < N) {
-            if (epi.bias) x += __ldg(epi.bias + col);
-            x = apply_act(x, epi.act);
-            if (epi.colscale) x *= __ldg(epi.colscale + col);
-          }
-          v[j] = x;
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stg + lane * 36 + j) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        __syncwarp();
+        if (c + 1 < n_chunks) tc5_ld_32x32(taddr0 + (c + 1) * 32, r);  // in flight while this chunk is stored
+        const float4 bb = *reinterpret_cast<const float4*>(sbias + c * 32 + c4);
+        float s4[4] = {1.f, 1.f, 1.f, 1.f};
+        if constexpr (KIND == E_F32_ACC || KIND == E_GENERIC) {
+          const float4 sc = *reinterpret_cast<const float4*>(sscale + c * 32 + c4);
+          s4[0] = sc.x; s4[1] = sc.y; s4[2] = sc.z; s4[3] = sc.w;
         }
-        if (!row_ok) continue;
-        const bool full = (col0 + 32 <= N);
-        if (epi.mode == M5_OUT_F32) {
-          float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldc + col0;
-          if (full) {
+        float4 prev[8];
+        if constexpr (KIND == E_F32_ACC) {
+          if (full4) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 w = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (epi.accumulate) {
-                const float4 p = *reinterpret_cast<const float4*>(o + j);
-                w.x += p.x; w.y += p.y; w.z += p.z; w.w += p.w;
-              }
-              *reinterpret_cast<float4*>(o + j) = w;
-            }
-          } else {
-            for (int j = 0; j < 32 && col0 + j < N; ++j) o[j] = epi.accumulate ? o[j] + v[j] : v[j];
-          }
-        } else if (epi.mode == M5_OUT_F16) {
-          __half* o = reinterpret_cast<__half*>(epi.out) + (size_t)row * epi.ldc + col0;
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 w;
-              w.x = pack_half2(v[j], v[j + 1]);
-              w.y = pack_half2(v[j + 2], v[j + 3]);
-              w.z = pack_half2(v[j + 4], v[j + 5]);
-              w.w = pack_half2(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(o + j) = w;
-            }
-          } else {
-            for (int j = 0; j < 32 && col0 + j < N; ++j) o[j] = __float2half_rn(v[j]);
-          }
-        } else if (epi.mode == M5_OUT_F16_SPLIT) {
-          __half* o = reinterpret_cast<__half*>(epi.out) + (size_t)row * epi.ldc + col0;
-          __half* ol = reinterpret_cast<__half*>(epi.out_lo) + (size_t)row * epi.ldc + col0;
-          for (int j = 0; j < 32 && col0 + j < N; ++j) {
-            const __half h = __float2half_rn(v[j]);
-            o[j] = h;
-            ol[j] = __float2half_rn(v[j] - __half2float(h));
-          }
-        } else {  // M5_OUT_SWIGLU_F16 / _SPLIT: columns (2j, 2j+1) = (W_j x, V_j x) -> silu(Wx) * Vx, N/2 outputs
-          const int ocol0 = col0 >> 1;
-          __half* o = reinterpret_cast<__half*>(epi.out) + (size_t)row * epi.ldc + ocol0;
-          float g[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = v[2 * j];
-            g[j] = (a / (1.0f + __expf(-a))) * v[2 * j + 1];
-          }
-          if (epi.mode == M5_OUT_SWIGLU_F16) {
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 8) {
-                uint4 w;
-                w.x = pack_half2(g[j], g[j + 1]);
-                w.y = pack_half2(g[j + 2], g[j + 3]);
-                w.z = pack_half2(g[j + 4], g[j + 5]);
-                w.w = pack_half2(g[j + 6], g[j + 7]);
-                *reinterpret_cast<uint4*>(o + j) = w;
-              }
-            } else {
-              for (int j = 0; j < 16 && col0 + 2 * j + 1 < N; ++j) o[j] = __float2half_rn(g[j]);
-            }
-          } else {
-            __half* ol = reinterpret_cast<__half*>(epi.out_lo) + (size_t)row * epi.ldc + ocol0;
-            for (int j = 0; j < 16 && col0 + 2 * j + 1 < N; ++j) {
-              const __half h = __float2half_rn(g[j]);
-              o[j] = h;
-              ol[j] = __float2half_rn(g[j] - __half2float(h));
+            for (int i = 0; i < 8; ++i) {
+              const int row = row_base + rsub + 4 * i;
+              prev[i] = row < M ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(epi.out) + (size_t)row * epi.ldc + col)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = rsub + 4 * i;
+          const int row = row_base + rl;
+          const float4 a4 = *reinterpret_cast<const float4*>(stg + rl * 36 + c4);
+          float v[4] = {a4.x + bb.x, a4.y + bb.y, a4.z + bb.z, a4.w + bb.w};
+          if (row < M && col < N) epi_store4<KIND>(epi, v, s4, prev[i], row, col, N, full4);
+        }
+        __syncwarp();  // every lane is done with the staging tile before the next chunk overwrites it
       }
       tc5_fence_before();
       __syncwarp();
@@ -304,18 +352,17 @@ static int make_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t 
   return r == CUDA_SUCCESS ? M5_OK : M5_ERR_CUDA;
 }
 
-template <int BLOCK_N>
-static int launch_bn(const GemmCall& g, cudaStream_t stream, int num_sms) {
+template <int BLOCK_N, int KIND>
+static int launch_kind(const GemmCall& g, cudaStream_t stream, int num_sms) {
   using S = GemmSmem<BLOCK_N>;
   CUtensorMap ta, tb;
-  const int Ka = g.awrap > 0 ? g.awrap : g.K;   // A's stored K extent
-  const int Kb = g.kwrap > 0 ? g.kwrap : g.K;  // W's K extent
+  const int Ka = g.awrap > 0 ? g.awrap : g.K;  // A's stored K extent
+  const int Kb = g.kwrap > 0 ? g.kwrap : g.K;  // W's stored K extent
   if (make_tmap(&ta, g.A, g.M, Ka, g.lda, BLOCK_M) != M5_OK) return M5_ERR_CUDA;
   if (make_tmap(&tb, g.W, g.N, Kb, g.ldw, BLOCK_N) != M5_OK) return M5_ERR_CUDA;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc5_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_tc5_kernel<BLOCK_N, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
       return M5_ERR_CUDA;
     attr_set = true;
   }
@@ -325,14 +372,27 @@ static int launch_bn(const GemmCall& g, cudaStream_t stream, int num_sms) {
   GemmEpi e;
   e.bias = g.bias; e.colscale = g.colscale; e.out = g.out; e.out_lo = g.out_lo; e.ldc = g.ldc;
   e.mode = g.mode; e.act = g.act; e.accumulate = g.accumulate;
-  gemm_tc5_kernel<BLOCK_N><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ta, tb, g.M, g.N, g.K, g.kwrap, g.awrap, e);
+  gemm_tc5_kernel<BLOCK_N, KIND><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ta, tb, g.M, g.N, g.K, g.kwrap, g.awrap, e);
   return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
+}
+
+template <int BLOCK_N>
+static int launch_bn(const GemmCall& g, cudaStream_t stream, int num_sms) {
+  const bool plain = g.act == M5_ACT_NONE;
+  if (plain && g.mode == M5_OUT_F32 && !g.accumulate && !g.colscale) return launch_kind<BLOCK_N, E_F32>(g, stream, num_sms);
+  if (plain && g.mode == M5_OUT_F32 && g.accumulate) return launch_kind<BLOCK_N, E_F32_ACC>(g, stream, num_sms);
+  if (plain && g.mode == M5_OUT_F16 && !g.colscale) return launch_kind<BLOCK_N, E_F16>(g, stream, num_sms);
+  if (plain && g.mode == M5_OUT_SWIGLU_F16 && !g.colscale) return launch_kind<BLOCK_N, E_SWIGLU>(g, stream, num_sms);
+  return launch_kind<BLOCK_N, E_GENERIC>(g, stream, num_sms);
 }
 
 int gemm_tc5(const GemmCall& g, cudaStream_t stream, int num_sms) {
   if (g.M <= 0 || g.N <= 0) return M5_OK;
   if (g.K % BLOCK_K != 0 || g.lda % 8 != 0 || g.ldw % 8 != 0) return M5_ERR_ARG;
-  if ((g.mode == M5_OUT_F32 && g.ldc % 4 != 0) || (g.mode != M5_OUT_F32 && g.ldc % 8 != 0)) return M5_ERR_ARG;
+  if ((g.kwrap > 0 && g.kwrap % BLOCK_K != 0) || (g.awrap > 0 && g.awrap % BLOCK_K != 0)) return M5_ERR_ARG;
+  if (g.mode == M5_OUT_F32 && g.ldc % 4 != 0) return M5_ERR_ARG;
+  if ((g.mode == M5_OUT_F16 || g.mode == M5_OUT_F16_SPLIT) && g.ldc % 4 != 0) return M5_ERR_ARG;
+  if ((g.mode == M5_OUT_SWIGLU_F16 || g.mode == M5_OUT_SWIGLU_F16_SPLIT) && (g.ldc % 2 != 0 || g.N % 2 != 0)) return M5_ERR_ARG;
   // Pick the N tile: 256 when it does not waste much, else 128 / 64.
   const int m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
   auto waste = [&](int bn) { return (double)(((g.N + bn - 1) / bn) * bn) / g.N; };
