@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--T", type=int, default=200)
     ap.add_argument("--precise", type=int, default=0)
+    ap.add_argument("--ntok", type=int, default=0, help="profiling aid: override the target-text token count (N = 15 * ntok)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -196,6 +197,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     small = args.size != "full"
     wl_kw = dict(n_text_tok=10, n_ref_tok=5, Pf=40, frames_per_tok=4) if small else {}
+    if args.ntok:
+        wl_kw["n_text_tok"] = args.ntok
     config = {"workload": f"deep-clone B={args.batch} Pf={wl_kw.get('Pf', 450)} text={wl_kw.get('n_text_tok', 100)}tok "
                           f"N={wl_kw.get('n_text_tok', 100) * wl_kw.get('frames_per_tok', 15)} T={args.T} CFG w=3 ({args.size} model, "
                           f"BASELINE configs[2])",

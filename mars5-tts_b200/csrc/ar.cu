@@ -216,7 +216,8 @@ static int ar_prefill_trunk(m5_ctx* ctx, const ArWeights& w, const ArPlan& p, fl
   return M5_OK;
 }
 
-static int run_skinny(m5_ctx* ctx, const SkinnyCall& s) {
+static int run_skinny(m5_ctx* ctx, SkinnyCall s) {
+  s.scratch = ctx->skinny_scratch; s.counters = ctx->skinny_counters;
   int r = gemm_skinny(s, ctx->stream, ctx->num_sms);
   if (r != M5_OK) return ctx->fail(r, "gemm_skinny failed (N=" + std::to_string(s.N) + " K=" + std::to_string(s.K) + ")");
   ctx->launches++;
@@ -359,7 +360,7 @@ int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int3
   const int Wc = max_len + 1;  // spk slot + every token that can ever be fed (sliding window 3000 never wraps, ar_generate.py:57)
   const int big = std::max(rows, spk_rows);
   const int ffmax = std::max(F, c.ar_spk_ff);
-  const int n_split = std::max(1, std::min(16, (4 * ctx->num_sms + B * c.ar_heads - 1) / (B * c.ar_heads)));
+  const int n_split = decode_attn_splits_for(Wc);
   Arena ar(ctx);
   const size_t cache_bytes = (size_t)2 * L * B * Wc * D * 2;
   const size_t noise_bytes = (noise && mem == M5_MEM_HOST) ? (size_t)B * noise_steps * V * 4 : 0;

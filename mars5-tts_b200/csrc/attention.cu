@@ -192,79 +192,100 @@ int flash_attn(const AttnCall& c, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Decode attention: one query per (row b, head h).  Grid (n_split, H, B); each CTA handles a contiguous
-// slice of the cached keys with 4 warps; every warp owns whole keys (lane = 2 of the 64 dims) so K/V rows are
-// read as fully coalesced 128-byte lines.  Partial (max, sum, acc[64]) per split are merged by a second kernel.
+// Decode attention: one query per (row b, head h).  Grid (n_split, H, B); split s owns keys [s*DA_KEYS, (s+1)*DA_KEYS)
+// (CTAs beyond the row's length exit at once, so the grid can be sized for the longest possible context and captured
+// in a CUDA graph).  8 lanes x 16-byte loads cover one 128-byte K (or V) row, a warp covers 4 keys per instruction and
+// keeps 4 such instructions in flight for K and for V; partial (max, sum, acc[64]) per split are merged by a second
+// kernel in a fixed order (deterministic).
 static constexpr int DA_THREADS = 128;
+static constexpr int DA_KEYS = 128;   // keys per CTA
 
 __global__ void __launch_bounds__(DA_THREADS)
 decode_attn_split_kernel(DecodeAttnCall p) {
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   if (p.done && p.done[b]) return;
   const int L = p.kv_len[b];
-  const int per = (L + p.n_split - 1) / p.n_split;
-  const int k0 = split * per, k1 = min(L, k0 + per);
+  const int k0 = split * DA_KEYS, k1 = min(L, k0 + DA_KEYS);
+  if (k0 >= L) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int sub = lane & 7, grp = lane >> 3;  // 8 lanes per key row, 4 keys per warp instruction
   const int D = p.H * HD;
-  const __half2 qh = *reinterpret_cast<const __half2*>(p.q + (size_t)b * D + h * HD + 2 * lane);
-  const float2 q = __half22float2(qh);
+  float q[8];
+  {
+    const uint4 qv = *reinterpret_cast<const uint4*>(p.q + (size_t)b * D + h * HD + sub * 8);
+    const __half2* qh = reinterpret_cast<const __half2*>(&qv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(qh[i]); q[2 * i] = f.x; q[2 * i + 1] = f.y; }
+  }
   const float sl2 = 0.125f * 1.4426950408889634f;
-  const __half* kb = p.kc + ((size_t)b * p.W) * D + h * HD + 2 * lane;
-  const __half* vb = p.vc + ((size_t)b * p.W) * D + h * HD + 2 * lane;
-  float m = -INFINITY, l = 0.f, ax = 0.f, ay = 0.f;
-  // 4 keys in flight per warp iteration
-  for (int k = k0 + warp * 4; k < k1; k += 4 * 4) {
-    float sc[4];
-    float2 vv[4];
+  const __half* kb = p.kc + ((size_t)b * p.W) * D + h * HD + sub * 8;
+  const __half* vb = p.vc + ((size_t)b * p.W) * D + h * HD + sub * 8;
+  float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  // each warp iteration covers 16 keys: key = kbase + u*4 + grp
+  for (int kbase = k0 + warp * 16; kbase < k1; kbase += 4 * 16) {
+    uint4 kv[4], vv[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int kk = k + u;
-      if (kk < k1) {
-        const float2 kf = __half22float2(*reinterpret_cast<const __half2*>(kb + (size_t)kk * D));
-        vv[u] = __half22float2(*reinterpret_cast<const __half2*>(vb + (size_t)kk * D));
-        sc[u] = q.x * kf.x + q.y * kf.y;
+      const int key = kbase + u * 4 + grp;
+      if (key < k1) {
+        kv[u] = *reinterpret_cast<const uint4*>(kb + (size_t)key * D);
+        vv[u] = *reinterpret_cast<const uint4*>(vb + (size_t)key * D);
       } else {
-        sc[u] = 0.f;
-        vv[u] = make_float2(0.f, 0.f);
+        kv[u] = make_uint4(0, 0, 0, 0);
+        vv[u] = make_uint4(0, 0, 0, 0);
       }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      float s = warp_sum(sc[u]);
-      if (k + u < k1) {
+      const int key = kbase + u * 4 + grp;
+      const __half2* kh = reinterpret_cast<const __half2*>(&kv[u]);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(kh[i]); s += q[2 * i] * f.x + q[2 * i + 1] * f.y; }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (key < k1) {
         s *= sl2;
         const float mn = fmaxf(m, s);
-        const float c = exp2f(m - mn);
-        const float pe = exp2f(s - mn);
+        const float c = exp2f(m - mn), pe = exp2f(s - mn);
         l = l * c + pe;
-        ax = ax * c + pe * vv[u].x;
-        ay = ay * c + pe * vv[u].y;
+        const __half2* vh = reinterpret_cast<const __half2*>(&vv[u]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(vh[i]);
+          acc[2 * i] = acc[2 * i] * c + pe * f.x;
+          acc[2 * i + 1] = acc[2 * i + 1] * c + pe * f.y;
+        }
         m = mn;
       }
     }
   }
-  // merge the 4 warps through smem
-  __shared__ float sm[4], sl[4], sa[4][HD];
-  if (lane == 0) { sm[warp] = m; sl[warp] = l; }
-  sa[warp][2 * lane] = ax;
-  sa[warp][2 * lane + 1] = ay;
+  // merge the 4 key groups of the warp, then the 4 warps through smem
+  __shared__ float sm[16], sl[16], sa[16][HD];
+  const int slot = warp * 4 + grp;
+  if (sub == 0) { sm[slot] = m; sl[slot] = l; }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sa[slot][sub * 8 + i] = acc[i];
   __syncthreads();
-  if (warp == 0) {
-    float M = fmaxf(fmaxf(sm[0], sm[1]), fmaxf(sm[2], sm[3]));
-    float Ls = 0.f, ox = 0.f, oy = 0.f;
+  if (tid < HD) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) M = fmaxf(M, sm[w]);
+    float Ls = 0.f, o = 0.f;
     if (M > -INFINITY) {
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
+      for (int w = 0; w < 16; ++w) {
         const float c = exp2f(sm[w] - M);
         Ls += sl[w] * c;
-        ox += sa[w][2 * lane] * c;
-        oy += sa[w][2 * lane + 1] * c;
+        o += sa[w][tid] * c;
       }
     }
     float* sp = p.scratch + ((size_t)(b * p.H + h) * p.n_split + split) * (HD + 2);
-    if (lane == 0) { sp[0] = M; sp[1] = Ls; }
-    sp[2 + 2 * lane] = ox;
-    sp[2 + 2 * lane + 1] = oy;
+    if (tid == 0) { sp[0] = M; sp[1] = Ls; }
+    sp[2 + tid] = o;
   }
 }
 
@@ -272,10 +293,11 @@ __global__ void decode_attn_merge_kernel(DecodeAttnCall p) {
   const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;  // 32 threads
   if (p.done && p.done[b]) return;
   const float* sp = p.scratch + ((size_t)(b * p.H + h) * p.n_split) * (HD + 2);
+  const int ns = min(p.n_split, (p.kv_len[b] + DA_KEYS - 1) / DA_KEYS);  // splits that own at least one key
   float M = -INFINITY;
-  for (int s = 0; s < p.n_split; ++s) M = fmaxf(M, sp[s * (HD + 2)]);
+  for (int s = 0; s < ns; ++s) M = fmaxf(M, sp[s * (HD + 2)]);
   float L = 0.f, ox = 0.f, oy = 0.f;
-  for (int s = 0; s < p.n_split; ++s) {
+  for (int s = 0; s < ns; ++s) {
     const float* q = sp + s * (HD + 2);
     if (q[0] == -INFINITY) continue;
     const float c = exp2f(q[0] - M);
@@ -288,6 +310,7 @@ __global__ void decode_attn_merge_kernel(DecodeAttnCall p) {
 }
 
 size_t decode_attn_scratch_bytes(int B, int H, int n_split) { return (size_t)B * H * n_split * (HD + 2) * sizeof(float); }
+int decode_attn_splits_for(int max_kv) { return (max_kv + DA_KEYS - 1) / DA_KEYS; }
 
 int decode_attn(const DecodeAttnCall& c, cudaStream_t stream) {
   if (c.B <= 0) return M5_OK;

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "rowops.h"
 
 namespace m5 {
@@ -101,6 +103,9 @@ int m5_create(int device, const m5_model_cfg* cfg, const m5_tensor* tensors, int
   for (int i = 0; i < 32; ++i) inv[i] = 1.0f / powf(10000.0f, (float)(2 * i) / 64.0f);
   cudaMalloc(&ctx->rope_inv_freq, sizeof(inv));
   cudaMemcpy(ctx->rope_inv_freq, inv, sizeof(inv), cudaMemcpyHostToDevice);
+  cudaMalloc(&ctx->skinny_scratch, gemm_skinny_scratch_bytes(ctx->num_sms));
+  cudaMalloc(&ctx->skinny_counters, 1024 * sizeof(int));
+  cudaMemset(ctx->skinny_counters, 0, 1024 * sizeof(int));
   // The caller may override the three derived tables with torch-computed ones (bit-exact with the reference):
   //   "tab.rope_inv_freq" [32], "tab.pe_ar" [max_pos, ar_dim], "tab.pe_nar" [max_pos, nar_dim]
   *out = ctx;
@@ -115,6 +120,8 @@ void m5_destroy(m5_ctx* ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->rope_inv_freq) cudaFree(ctx->rope_inv_freq);
   if (ctx->twiddle) cudaFree(ctx->twiddle);
+  if (ctx->skinny_scratch) cudaFree(ctx->skinny_scratch);
+  if (ctx->skinny_counters) cudaFree(ctx->skinny_counters);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -194,6 +201,7 @@ int m5_dbg_attn(m5_ctx* ctx, const void* Q, const void* K, const void* V, int32_
 int m5_dbg_decode_attn(m5_ctx* ctx, const void* q, const void* kc, const void* vc, int32_t B, int32_t H, int32_t W,
                        const int32_t* kv_len, void* out, int32_t n_split) {
   if (!ctx) return M5_ERR_ARG;
+  n_split = std::max(n_split, decode_attn_splits_for(W));  // the kernel owns a fixed 128-key slice per split
   Arena ar(ctx);
   M5_TRY(ar.reserve(decode_attn_scratch_bytes(B, H, n_split) + 4096));
   DecodeAttnCall c;

@@ -36,6 +36,8 @@ struct m5_ctx {
   float* pe_ar = nullptr;          // [max_pos, ar_dim]
   float* pe_nar = nullptr;         // [max_pos, nar_dim]
   float* twiddle = nullptr;        // iSTFT tables
+  float* skinny_scratch = nullptr; // split-K partial tiles of the decode GEMMs
+  int* skinny_counters = nullptr;  // [1024] tickets
 
   int fail(int code, const std::string& msg) {
     last_error = msg;

@@ -41,7 +41,10 @@ struct SkinnyCall {
   int ldc = 0;
   int swiglu = 0;
   int accumulate = 0;
+  float* scratch = nullptr;  // split-K partial tiles (ctx-owned, gemm_skinny_scratch_bytes)
+  int* counters = nullptr;   // one ticket per 128-row tile, zero between launches
 };
+size_t gemm_skinny_scratch_bytes(int num_sms);
 int gemm_skinny(const SkinnyCall& c, cudaStream_t stream, int num_sms);
 
 // ---- row kernels (rowops.cu) -------------------------------------------------------------------
@@ -90,5 +93,6 @@ struct DecodeAttnCall {
 };
 int decode_attn(const DecodeAttnCall& c, cudaStream_t stream);
 size_t decode_attn_scratch_bytes(int B, int H, int n_split);
+int decode_attn_splits_for(int max_kv);  // n_split needed so that every key of a context of max_kv is covered
 
 }  // namespace m5

@@ -66,9 +66,79 @@ __global__ void __launch_bounds__(256) norm_rows_kernel(NormCall p) {
   }
 }
 
+// Few rows (AR decode: M = batch): one CTA per row so that the whole row is in flight at once (latency-bound case).
+__global__ void __launch_bounds__(256) norm_row_cta_kernel(NormCall p) {
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int src = p.row_map ? p.row_map[row] : row;
+  const float* x = p.x + (size_t)src * p.ldx;
+  const int D = p.D, nv = D >> 2;
+  __shared__ float red[2][8];
+  float4 v[2];
+  float s = 0.f, ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int i = tid + j * 256;
+    v[j] = i < nv ? *reinterpret_cast<const float4*>(x + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += v[j].x + v[j].y + v[j].z + v[j].w;
+    ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+  }
+  s = warp_sum(s); ss = warp_sum(ss);
+  if ((tid & 31) == 0) { red[0][tid >> 5] = s; red[1][tid >> 5] = ss; }
+  __syncthreads();
+  s = 0.f; ss = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { s += red[0][w]; ss += red[1][w]; }
+  float mean = 0.f, rstd;
+  if (p.rms) {
+    rstd = rsqrtf(ss / D + p.eps);
+  } else {
+    mean = s / D;
+    float vs = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (tid + j * 256 < nv) {
+        const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+        vs += a * a + b * b + c * c + d * d;
+      }
+    }
+    vs = warp_sum(vs);
+    __syncthreads();
+    if ((tid & 31) == 0) red[0][tid >> 5] = vs;
+    __syncthreads();
+    vs = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) vs += red[0][w];
+    rstd = rsqrtf(vs / D + p.eps);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int i = 4 * (tid + j * 256);
+    if (i >= D) continue;
+    float y[4] = {(v[j].x - mean) * rstd, (v[j].y - mean) * rstd, (v[j].z - mean) * rstd, (v[j].w - mean) * rstd};
+    if (p.gamma) { const float4 gm = *reinterpret_cast<const float4*>(p.gamma + i); y[0] *= gm.x; y[1] *= gm.y; y[2] *= gm.z; y[3] *= gm.w; }
+    if (p.beta) { const float4 bt = *reinterpret_cast<const float4*>(p.beta + i); y[0] += bt.x; y[1] += bt.y; y[2] += bt.z; y[3] += bt.w; }
+    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ldo + i) = make_float4(y[0], y[1], y[2], y[3]);
+    if (p.out) {
+      const __half h0 = __float2half_rn(y[0]), h1 = __float2half_rn(y[1]), h2 = __float2half_rn(y[2]), h3 = __float2half_rn(y[3]);
+      __half2* o = reinterpret_cast<__half2*>(p.out + (size_t)row * p.ldo + i);
+      o[0] = __halves2half2(h0, h1);
+      o[1] = __halves2half2(h2, h3);
+      if (p.out_lo) {
+        __half2* ol = reinterpret_cast<__half2*>(p.out_lo + (size_t)row * p.ldo + i);
+        ol[0] = __floats2half2_rn(y[0] - __half2float(h0), y[1] - __half2float(h1));
+        ol[1] = __floats2half2_rn(y[2] - __half2float(h2), y[3] - __half2float(h3));
+      }
+    }
+  }
+}
+
 int norm_rows(const NormCall& c, cudaStream_t stream) {
   if (c.M <= 0) return M5_OK;
   if (c.D % 4 != 0 || c.ldx % 4 != 0 || c.ldo % 4 != 0) return M5_ERR_ARG;
+  if (c.M <= 64 && c.D <= 2048) {
+    norm_row_cta_kernel<<<c.M, 256, 0, stream>>>(c);
+    return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
+  }
   const int wpb = 8;
   norm_rows_kernel<<<(c.M + wpb - 1) / wpb, wpb * 32, 0, stream>>>(c);
   return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;

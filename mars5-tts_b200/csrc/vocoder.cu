@@ -183,7 +183,7 @@ int m5_dbg_skinny(m5_ctx* ctx, const void* X, const void* Wt, int32_t B, int32_t
   if (!ctx) return M5_ERR_ARG;
   SkinnyCall s;
   s.X = (const __half*)X; s.W = (const __half*)Wt; s.B = B; s.N = N; s.K = K; s.out_f32 = out_f32; s.out_f16 = (__half*)out_f16;
-  s.ldc = ldc; s.swiglu = swiglu; s.accumulate = accumulate;
+  s.ldc = ldc; s.swiglu = swiglu; s.accumulate = accumulate; s.scratch = ctx->skinny_scratch; s.counters = ctx->skinny_counters;
   int r = gemm_skinny(s, ctx->stream, ctx->num_sms);
   if (r != M5_OK) return ctx->fail(r, "gemm_skinny failed");
   ctx->launches++;
