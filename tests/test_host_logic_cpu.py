@@ -1,0 +1,46 @@
+"""CPU suite: host-side logic that needs no GPU (weight repack layout, schedule tables, tokenizer stand-ins, bench workload)."""
+import numpy as np
+import torch
+
+from mars5_tts_b200 import synth, weights
+
+
+def test_repack_layouts():
+    size = synth.TINY
+    ar, nar, voc = synth.make_ar_state(size), synth.make_nar_state(size), synth.make_vocos_state(size)
+    d = weights.dims_from_state(ar, nar, voc, size["n_text"])
+    t, alphas = weights.repack(ar, nar, voc, d, max_pos=64)
+    D, F = d["ar_dim"], d["ar_hidden"]
+    assert t["ar.l0.wqkv"].shape == (3 * D, D) and t["ar.l0.wqkv"].dtype == torch.float16
+    assert torch.equal(t["ar.l0.wqkv"][D:2 * D].float(), ar["ar.layers.0.attention.wk.weight"])  # fp16-exact checkpoints
+    w13 = t["ar.l0.w13"].float()
+    assert torch.equal(w13[0::2], ar["ar.layers.0.feed_forward.w1.weight"]) and torch.equal(w13[1::2], ar["ar.layers.0.feed_forward.w3.weight"])
+    Dn = d["nar_dim"]
+    assert torch.equal(t["nar.dec.l1.ca_kv_w"].float(), nar["tfm.decoder.layers.1.multihead_attn.in_proj_weight"][Dn:])
+    hw = voc["head.out.weight"]
+    h3 = t["voc.head_w"].float()
+    K = hw.shape[1]
+    assert (h3[:, :K] + h3[:, 2 * K:] - hw).abs().max() < 1e-6 and torch.equal(h3[:, :K], h3[:, K:2 * K])
+    assert abs(alphas["ar_pos_alpha"] - 0.75) < 1e-6
+    cfg = weights.make_cfg(d, alphas, 64)
+    assert cfg.ar_layers == size["ar_layers"] and abs(cfg.ln_eps - 4e-5) < 1e-9
+
+
+def test_pe_and_timestep_tables_match_reference_formulas():
+    pe = weights.sine_pe(50, 128)
+    pos = torch.arange(50, dtype=torch.float32)[:, None]
+    div = torch.exp(torch.arange(0, 128, 2, dtype=torch.float32) * -(np.log(10000.0) / 128))
+    assert torch.equal(pe[:, 0::2], torch.sin(pos * div)) and torch.equal(pe[:, 1::2], torch.cos(pos * div))
+    tt = weights.timestep_table(10, 128)
+    assert tt.shape == (10, 128) and torch.allclose(tt[0, :64], torch.ones(64)) and torch.allclose(tt[0, 64:], torch.zeros(64))
+
+
+def test_synthetic_tokenizers_and_bench_workload():
+    tt, st = synth.ByteTextTok(), synth.CodeSpeechTok()
+    ids = tt.encode("<|startoftext|>hi<|endoftext|>")
+    assert ids == [256, ord("h"), ord("i"), 257] and len(tt.vocab) == 258 and len(st.vocab) == 1025
+    assert st.encode("3 7 1023") == [3, 7, 1023] and st.decode_int([5, 1024, 9]) == [5, 9]
+    import bench
+    wl = bench.make_workload(synth.FULL, 2, 0)
+    assert wl["N"] == 1500 and len(wl["prompts"][0]) == 137 + 450 and wl["first_codec_idx"] == 138
+    assert abs(wl["audio_s"] - 2 * 1499 / 75) < 1e-9 and wl["max_len"] == 587 + 1502
