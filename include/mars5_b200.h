@@ -157,7 +157,8 @@ int m5_dbg_norm(m5_ctx* ctx, const float* x, int32_t M, int32_t D, const float* 
                 int32_t rms, void* out_f16, void* out_lo_f16);
 int m5_dbg_attn(m5_ctx* ctx, const void* Q, const void* K, const void* V, int32_t ldq, int32_t ldk, int32_t ldv,
                 void* O, int32_t ldo, int32_t n_heads, int32_t n_seqs, int32_t max_q, const int32_t* q_start,
-                const int32_t* q_len, const int32_t* k_start, const int32_t* k_len, int32_t causal);
+                const int32_t* q_len, const int32_t* k_start, const int32_t* k_len, int32_t causal, int32_t impl,
+                int32_t q_rows, int32_t k_rows); /* impl: 1 = mma.sync kernel, 2 = tcgen05 kernel (needs q_rows/k_rows) */
 int m5_dbg_decode_attn(m5_ctx* ctx, const void* q, const void* kc, const void* vc, int32_t B, int32_t H, int32_t W,
                        const int32_t* kv_len, void* out, int32_t n_split);
 /* AR sampler chain on fp32 logits [B][V] (ar_generate.py:73-118): writes the chosen token per row. */

@@ -61,7 +61,7 @@ _SIGS = {
     "m5_dbg_gemm": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I]),
     "m5_dbg_skinny": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _I]),
     "m5_dbg_norm": (_I, [_P, _P, _I, _I, _P, _P, C.c_float, _I, _P, _P]),
-    "m5_dbg_attn": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I]),
+    "m5_dbg_attn": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I]),
     "m5_dbg_decode_attn": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I]),
     "m5_dbg_sample": (_I, [_P, _P, _I, _I, C.POINTER(ArCfg), _I, _P, _I, _P, _P, _P, C.c_uint64, _P, _P]),
     "m5_dbg_posterior": (_I, [_P, _P, _P, _I, _I, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, C.c_uint64, _P]),

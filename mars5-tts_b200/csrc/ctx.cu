@@ -186,13 +186,14 @@ int m5_dbg_norm(m5_ctx* ctx, const float* x, int32_t M, int32_t D, const float* 
 
 int m5_dbg_attn(m5_ctx* ctx, const void* Q, const void* K, const void* V, int32_t ldq, int32_t ldk, int32_t ldv,
                 void* O, int32_t ldo, int32_t n_heads, int32_t n_seqs, int32_t max_q, const int32_t* q_start,
-                const int32_t* q_len, const int32_t* k_start, const int32_t* k_len, int32_t causal) {
+                const int32_t* q_len, const int32_t* k_start, const int32_t* k_len, int32_t causal, int32_t impl,
+                int32_t q_rows, int32_t k_rows) {
   if (!ctx) return M5_ERR_ARG;
   AttnCall c;
   c.Q = (const __half*)Q; c.K = (const __half*)K; c.V = (const __half*)V; c.ldq = ldq; c.ldk = ldk; c.ldv = ldv;
   c.O = (__half*)O; c.ldo = ldo; c.n_heads = n_heads; c.n_seqs = n_seqs; c.max_q = max_q; c.q_start = q_start;
-  c.q_len = q_len; c.k_start = k_start; c.k_len = k_len; c.causal = causal;
-  int r = flash_attn(c, ctx->stream);
+  c.q_len = q_len; c.k_start = k_start; c.k_len = k_len; c.causal = causal; c.q_rows = q_rows; c.k_rows = k_rows;
+  int r = impl == 2 ? flash_attn_tc5(c, ctx->stream) : flash_attn(c, ctx->stream);
   if (r != M5_OK) return ctx->fail(r, "flash_attn failed");
   ctx->launches += 1;
   return M5_OK;

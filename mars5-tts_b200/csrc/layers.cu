@@ -23,7 +23,8 @@ int run_norm(m5_ctx* ctx, const NormCall& n) {
 }
 int run_attn(m5_ctx* ctx, const AttnCall& a) {
   cudaEvent_t pe = prof_begin(ctx);
-  int r = flash_attn(a, ctx->stream);
+  const bool tc5 = a.impl == 2 || (a.impl == 0 && !a.causal && a.q_rows > 0 && a.k_rows > 0 && a.max_q >= 256);
+  int r = tc5 ? flash_attn_tc5(a, ctx->stream) : flash_attn(a, ctx->stream);
   if (pe) prof_end(ctx, pe, 1, a.flops_hint, 0.0);
   if (r != M5_OK) return ctx->fail(r, "flash_attn failed");
   ctx->launches += 1;
@@ -110,7 +111,7 @@ int encoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const EncLayerW& w,
   a.Q = s.qkv16; a.K = s.qkv16 + D; a.V = s.qkv16 + 2 * D; a.ldq = a.ldk = a.ldv = 3 * D;
   a.O = s.att16; a.ldo = D; a.n_heads = H; a.n_seqs = seqs.n; a.max_q = seqs.max_len;
   a.q_start = seqs.start; a.q_len = seqs.len; a.k_start = seqs.start; a.k_len = seqs.klen ? seqs.klen : seqs.len;
-  a.flops_hint = 256.0 * H * seqs.self_pairs;
+  a.flops_hint = 256.0 * H * seqs.self_pairs; a.q_rows = rows; a.k_rows = rows;
   M5_TRY(run_attn(ctx, a));
   GemmCall go = lin(s.att16, rows, D, false, w.out_w, D, w.out_b);
   go.out = x; go.ldc = D; go.mode = M5_OUT_F32; go.accumulate = 1;
@@ -131,7 +132,7 @@ int decoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const __half* mem16
   a.Q = s.qkv16; a.K = s.qkv16 + D; a.V = s.qkv16 + 2 * D; a.ldq = a.ldk = a.ldv = 3 * D;
   a.O = s.att16; a.ldo = D; a.n_heads = H; a.n_seqs = seqs.n; a.max_q = seqs.max_len;
   a.q_start = seqs.start; a.q_len = seqs.len; a.k_start = seqs.start; a.k_len = seqs.len;
-  a.flops_hint = 256.0 * H * seqs.self_pairs;
+  a.flops_hint = 256.0 * H * seqs.self_pairs; a.q_rows = rows; a.k_rows = rows;
   M5_TRY(run_attn(ctx, a));
   GemmCall go = lin(s.att16, rows, D, false, w.sa_out_w, D, w.sa_out_b);
   go.out = x; go.ldc = D; go.mode = M5_OUT_F32; go.accumulate = 1;
@@ -148,7 +149,7 @@ int decoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const __half* mem16
   c.Q = s.qkv16; c.ldq = D; c.K = s.kv16; c.V = s.kv16 + D; c.ldk = c.ldv = 2 * D;
   c.O = s.att16; c.ldo = D; c.n_heads = H; c.n_seqs = seqs.n; c.max_q = seqs.max_len;
   c.q_start = seqs.start; c.q_len = seqs.len; c.k_start = mem_seqs.start; c.k_len = mem_seqs.len;
-  c.flops_hint = 256.0 * H * seqs.cross_pairs;
+  c.flops_hint = 256.0 * H * seqs.cross_pairs; c.q_rows = rows; c.k_rows = mem_seqs.rows;
   M5_TRY(run_attn(ctx, c));
   GemmCall gco = lin(s.att16, rows, D, false, w.ca_out_w, D, w.ca_out_b);
   gco.out = x; gco.ldc = D; gco.mode = M5_OUT_F32; gco.accumulate = 1;

@@ -77,8 +77,11 @@ struct AttnCall {
   int causal = 0;  // key j visible to query i iff j <= i + (k_len - q_len)
   float scale = 0.125f;
   double flops_hint = 0.0;  // 4 * 64 * heads * sum_s(q_len*k_len) (halved when causal); profiling only
+  int q_rows = 0, k_rows = 0;  // total rows of the Q and K/V buffers (TMA bounds); required by the tcgen05 kernel
+  int impl = 0;                // 0 auto, 1 mma.sync kernel, 2 tcgen05 kernel
 };
-int flash_attn(const AttnCall& c, cudaStream_t stream);
+int flash_attn(const AttnCall& c, cudaStream_t stream);      // mma.sync (causal prefill, tiny problems)
+int flash_attn_tc5(const AttnCall& c, cudaStream_t stream);  // tcgen05 / TMEM (attention_tc5.cu)
 
 // Single-query attention over the fp16 KV cache of the AR model (decode step).
 struct DecodeAttnCall {

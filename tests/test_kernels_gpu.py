@@ -139,8 +139,8 @@ def _attn_ref(q, k, v, causal):
     return torch.einsum("hqk,khd->qhd", p, v)
 
 
-@pytest.mark.parametrize("causal", [0, 1])
-def test_flash_attn_varlen(m5lib, bare_ctx, causal):
+@pytest.mark.parametrize("causal,impl", [(0, 1), (1, 1), (0, 2)])
+def test_flash_attn_varlen(m5lib, bare_ctx, causal, impl):
     g = torch.Generator(device="cpu").manual_seed(7 + causal)
     H = 16
     q_lens = [1, 63, 64, 65, 200, 451]
@@ -158,7 +158,8 @@ def test_flash_attn_varlen(m5lib, bare_ctx, causal):
     else:
         Kp, Vp, ldk = KV, KV[:, D:], 2 * D
     rc = m5lib.m5_dbg_attn(bare_ctx, ptr(Q), C.c_void_p(Kp.data_ptr()), C.c_void_p(Vp.data_ptr()), 3 * D, ldk, ldk,
-                           ptr(O), D, H, len(q_lens), max(q_lens), ptr(qs), ptr(ql), ptr(ks), ptr(kl), causal)
+                           ptr(O), D, H, len(q_lens), max(q_lens), ptr(qs), ptr(ql), ptr(ks), ptr(kl), causal, impl,
+                           sum(q_lens), sum(q_lens) if causal else sum(k_lens))
     capi.check(bare_ctx, rc, "attn")
     _sync(m5lib, bare_ctx)
     for i in range(len(q_lens)):
