@@ -18,9 +18,9 @@
 // awrap > 0 -> A re-read modulo awrap against W = [W_hi | W_hi | W_lo]: fp32-class accuracy at 2-3x the tensor work.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
-#include "m5_internal.h"
-#include "ptx.cuh"
+#include "gemm_common.cuh"
 
 namespace m5 {
 
@@ -29,9 +29,6 @@ static constexpr int BLOCK_K = 64;  // 64 fp16 = one 128-byte swizzle row
 static constexpr int UMMA_K = 16;
 static constexpr int GEMM_THREADS = 192;
 static constexpr int M_BAND = 148;  // M-tiles kept L2-resident per sweep over N
-
-// epilogue kinds (compile-time)
-enum { E_F32 = 0, E_F32_ACC = 1, E_F16 = 2, E_SWIGLU = 3, E_GENERIC = 4 };
 
 template <int BLOCK_N>
 struct GemmSmem {
@@ -46,99 +43,6 @@ struct GemmSmem {
   static constexpr int BIAS_BYTES = 4 * 2 * BLOCK_N * 4;
   static constexpr int TOTAL = BIAS_OFF + BIAS_BYTES + 1024;  // + alignment slack
 };
-
-struct GemmEpi {
-  const float* bias;      // [N] fp32 or null
-  const float* colscale;  // [N] fp32 or null (Vocos layer-scale gamma)
-  void* out;              // fp32 or fp16, row stride ldc (elements)
-  void* out_lo;           // split modes: low halves
-  int ldc;
-  int mode;        // M5_OUT_*
-  int act;         // M5_ACT_*
-  int accumulate;  // fp32 out: out += value (residual stream update)
-};
-
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
-}
-__device__ __forceinline__ float silu_f(float a) { return __fdividef(a, 1.0f + __expf(-a)); }  // 2 MUFU + 2 FP ops
-
-// Stores 4 consecutive columns [col, col+4) of one row. v already holds accumulator + bias.
-template <int KIND>
-__device__ __forceinline__ void epi_store4(const GemmEpi& epi, float (&v)[4], const float (&s4)[4], const float4& prev, int row,
-                                           int col, int N, bool full4) {
-  if constexpr (KIND == E_F32 || KIND == E_F32_ACC) {
-    float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldc + col;
-    if constexpr (KIND == E_F32_ACC) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] *= s4[e];
-    }
-    if (full4) {
-      float4 w = make_float4(v[0], v[1], v[2], v[3]);
-      if constexpr (KIND == E_F32_ACC) { w.x += prev.x; w.y += prev.y; w.z += prev.z; w.w += prev.w; }
-      *reinterpret_cast<float4*>(o) = w;
-    } else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (col + e < N) o[e] = (KIND == E_F32_ACC) ? o[e] + v[e] : v[e];
-    }
-  } else if constexpr (KIND == E_F16) {
-    __half* o = reinterpret_cast<__half*>(epi.out) + (size_t)row * epi.ldc + col;
-    const __half h0 = __float2half_rn(v[0]), h1 = __float2half_rn(v[1]), h2 = __float2half_rn(v[2]), h3 = __float2half_rn(v[3]);
-    if (full4) {
-      *reinterpret_cast<uint2*>(o) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
-    } else {
-      if (col + 0 < N) o[0] = h0;
-      if (col + 1 < N) o[1] = h1;
-      if (col + 2 < N) o[2] = h2;
-    }
-  } else if constexpr (KIND == E_SWIGLU) {
-    // columns (2j, 2j+1) = (W_j x, V_j x) -> silu(W x) * V x ; N is even
-    __half* o = reinterpret_cast<__half*>(epi.out) + (size_t)row * epi.ldc + (col >> 1);
-    const __half h0 = __float2half_rn(silu_f(v[0]) * v[1]), h1 = __float2half_rn(silu_f(v[2]) * v[3]);
-    if (full4) *reinterpret_cast<uint32_t*>(o) = pack_h2(h0, h1);
-    else if (col + 1 < N) o[0] = h0;
-  } else {  // E_GENERIC: activations, column scale, split (hi | lo) outputs -- cold paths (vocoder, timestep MLPs, precise mode)
-    if (epi.act == M5_ACT_GELU) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = 0.5f * v[e] * (1.0f + erff(v[e] * 0.70710678118654752440f));
-    } else if (epi.act == M5_ACT_SILU) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = silu_f(v[e]);
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] *= s4[e];
-    if (epi.mode == M5_OUT_F32) {
-      float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldc + col;
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (col + e < N) o[e] = epi.accumulate ? o[e] + v[e] : v[e];
-    } else if (epi.mode == M5_OUT_F16 || epi.mode == M5_OUT_F16_SPLIT) {
-      __half* o = reinterpret_cast<__half*>(epi.out) + (size_t)row * epi.ldc + col;
-      __half* ol = reinterpret_cast<__half*>(epi.out_lo) + (size_t)row * epi.ldc + col;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (col + e < N) {
-          const __half h = __float2half_rn(v[e]);
-          o[e] = h;
-          if (epi.mode == M5_OUT_F16_SPLIT) ol[e] = __float2half_rn(v[e] - __half2float(h));
-        }
-      }
-    } else {  // SwiGLU (optionally split)
-      __half* o = reinterpret_cast<__half*>(epi.out) + (size_t)row * epi.ldc + (col >> 1);
-      __half* ol = reinterpret_cast<__half*>(epi.out_lo) + (size_t)row * epi.ldc + (col >> 1);
-      const float g[2] = {silu_f(v[0]) * v[1], silu_f(v[2]) * v[3]};
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        if (col + 2 * e + 1 < N) {
-          const __half h = __float2half_rn(g[e]);
-          o[e] = h;
-          if (epi.mode == M5_OUT_SWIGLU_F16_SPLIT) ol[e] = __float2half_rn(g[e] - __half2float(h));
-        }
-      }
-    }
-  }
-}
 
 template <int BLOCK_N, int KIND>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -339,44 +243,14 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
-// ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// 2-D fp16 row-major [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle.
-static int make_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return M5_ERR_CUDA;
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld * 2};
-  cuuint32_t box[2] = {BLOCK_K, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? M5_OK : M5_ERR_CUDA;
-}
-
 template <int BLOCK_N, int KIND>
 static int launch_kind(const GemmCall& g, cudaStream_t stream, int num_sms) {
   using S = GemmSmem<BLOCK_N>;
   CUtensorMap ta, tb;
   const int Ka = g.awrap > 0 ? g.awrap : g.K;  // A's stored K extent
   const int Kb = g.kwrap > 0 ? g.kwrap : g.K;  // W's stored K extent
-  if (make_tmap(&ta, g.A, g.M, Ka, g.lda, BLOCK_M) != M5_OK) return M5_ERR_CUDA;
-  if (make_tmap(&tb, g.W, g.N, Kb, g.ldw, BLOCK_N) != M5_OK) return M5_ERR_CUDA;
+  if (make_tmap_k64(&ta, g.A, g.M, Ka, g.lda, BLOCK_M) != M5_OK) return M5_ERR_CUDA;
+  if (make_tmap_k64(&tb, g.W, g.N, Kb, g.ldw, BLOCK_N) != M5_OK) return M5_ERR_CUDA;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_tc5_kernel<BLOCK_N, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
@@ -410,9 +284,13 @@ int gemm_tc5(const GemmCall& g, cudaStream_t stream, int num_sms) {
   if (g.mode == M5_OUT_F32 && g.ldc % 4 != 0) return M5_ERR_ARG;
   if ((g.mode == M5_OUT_F16 || g.mode == M5_OUT_F16_SPLIT) && g.ldc % 4 != 0) return M5_ERR_ARG;
   if ((g.mode == M5_OUT_SWIGLU_F16 || g.mode == M5_OUT_SWIGLU_F16_SPLIT) && (g.ldc % 2 != 0 || g.N % 2 != 0)) return M5_ERR_ARG;
-  // Pick the N tile: 256 when it does not waste much, else 128 / 64.
   const int m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
   auto waste = [&](int bn) { return (double)(((g.N + bn - 1) / bn) * bn) / g.N; };
+  // Large problems run on CTA pairs (cta_group::2, 256 x 256 tiles): halves the operand bytes each SM has to ingest.
+  static const bool no_pairs = getenv("M5_DISABLE_2CTA") != nullptr;
+  const bool pair_ok = !no_pairs && g.N >= 256 && waste(256) <= 1.12 && (long)((g.M + 255) / 256) * ((g.N + 255) / 256) >= num_sms / 2;
+  if (g.force_bn == 512 || (g.force_bn == 0 && pair_ok)) return gemm_tc5_2cta(g, stream, num_sms);
+  // Pick the N tile: 256 when it does not waste much, else 128 / 64.
   int bn = 256;
   if (g.N <= 64) bn = 64;
   else if (g.N <= 128) bn = 128;

@@ -36,7 +36,8 @@ def _gemm(lib, ctx, A, W, *, bias=None, colscale=None, mode=capi.OUT_F32, act=0,
 
 @pytest.mark.parametrize("M,N,K,bn", [(128, 256, 64, 0), (128, 128, 128, 128), (300, 1025, 1024, 0),
                                       (4096, 3072, 1024, 0), (586, 4608, 1536, 0), (77, 384, 1152, 0),
-                                      (1000, 64, 128, 64), (2500, 6144, 1024, 256)])
+                                      (1000, 64, 128, 64), (2500, 6144, 1024, 256), (2500, 6144, 1024, 512),
+                                      (300, 1025, 1024, 512), (128, 256, 64, 512), (40000, 3072, 1024, 0)])
 def test_gemm_f32(m5lib, bare_ctx, M, N, K, bn):
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
     A = (torch.randn(M, K, generator=g) * 0.5).half().to(DEV)

@@ -38,6 +38,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "one":
 for (N, K, mode, acc) in [(3072, 1024, capi.OUT_F16, 0), (1024, 1024, capi.OUT_F32, 1), (1024, 1024, capi.OUT_F16, 0), (6144, 1024, capi.OUT_SWIGLU_F16, 0),
                           (1024, 3072, capi.OUT_F32, 1), (1024, 3072, capi.OUT_F32, 0), (2048, 1024, capi.OUT_F16, 0), (1025, 1024, capi.OUT_F32, 0)]:
     bench(M, N, K, mode, acc)
+for (N, K, mode, acc) in [(3072, 1024, capi.OUT_F16, 0), (1024, 1024, capi.OUT_F32, 1), (6144, 1024, capi.OUT_SWIGLU_F16, 0), (1024, 3072, capi.OUT_F32, 1)]:
+    bench(M, N, K, mode, acc, bn=256)
 bench(M, 3072, 1024, capi.OUT_F16, 0, bn=128)
 bench(4352, 3072, 1024, capi.OUT_F16, 0)
 bench(18784, 4608, 1536, capi.OUT_F16, 0)
