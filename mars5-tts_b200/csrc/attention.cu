@@ -30,6 +30,9 @@ __device__ __forceinline__ void load_tile_async(__half* dst, const __half* src, 
   }
 }
 
+// PREC: every fp16 operand carries a low half (x = hi + lo): S = Qhi Khi + Qlo Khi + Qhi Klo, O = Phi Vhi + Plo Vhi + Phi Vlo
+// (three MMAs per product, fp32-class accuracy); the output is written as (hi, lo) as well.
+template <bool PREC>
 __global__ void __launch_bounds__(FA_THREADS)
 flash_attn_kernel(AttnCall p) {
   const int seq = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
@@ -39,24 +42,36 @@ flash_attn_kernel(AttnCall p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
 
-  __shared__ __align__(128) __half sQ[FA_BQ * HD];
-  __shared__ __align__(128) __half sK[2][FA_BK * HD];
-  __shared__ __align__(128) __half sV[2][FA_BK * HD];
+  extern __shared__ __align__(128) uint8_t fa_smem[];
+  constexpr int TILE = FA_BQ * HD;  // halves per 64x64 tile
+  __half* sQ = reinterpret_cast<__half*>(fa_smem);
+  __half* sK = sQ + TILE;            // [2][TILE]
+  __half* sV = sK + 2 * TILE;        // [2][TILE]
+  __half* sQl = sV + 2 * TILE;       // PREC only
+  __half* sKl = sQl + TILE;
+  __half* sVl = sKl + 2 * TILE;
 
-  const __half* Qg = p.Q + (size_t)(p.q_start[seq] + q0) * p.ldq + head * HD;
-  const __half* Kg = p.K + (size_t)p.k_start[seq] * p.ldk + head * HD;
-  const __half* Vg = p.V + (size_t)p.k_start[seq] * p.ldv + head * HD;
+  const size_t qoff = (size_t)(p.q_start[seq] + q0) * p.ldq + head * HD;
+  const size_t koff = (size_t)p.k_start[seq] * p.ldk + head * HD;
+  const size_t voff = (size_t)p.k_start[seq] * p.ldv + head * HD;
   const int q_valid = min(FA_BQ, q_len - q0);
   const int causal_off = k_len - q_len;
   int k_end = k_len;  // keys this CTA must visit
   if (p.causal) k_end = min(k_len, q0 + q_valid + causal_off);
   const int n_tiles = (k_end + FA_BK - 1) / FA_BK;
 
-  load_tile_async(sQ, Qg, p.ldq, q_valid, tid);
-  if (n_tiles > 0) {
-    load_tile_async(sK[0], Kg, p.ldk, min(FA_BK, k_end), tid);
-    load_tile_async(sV[0], Vg, p.ldv, min(FA_BK, k_end), tid);
-  }
+  auto load_kv = [&](int buf, int kn) {
+    const int rows = min(FA_BK, k_end - kn);
+    load_tile_async(sK + buf * TILE, p.K + koff + (size_t)kn * p.ldk, p.ldk, rows, tid);
+    load_tile_async(sV + buf * TILE, p.V + voff + (size_t)kn * p.ldv, p.ldv, rows, tid);
+    if constexpr (PREC) {
+      load_tile_async(sKl + buf * TILE, p.Klo + koff + (size_t)kn * p.ldk, p.ldk, rows, tid);
+      load_tile_async(sVl + buf * TILE, p.Vlo + voff + (size_t)kn * p.ldv, p.ldv, rows, tid);
+    }
+  };
+  load_tile_async(sQ, p.Q + qoff, p.ldq, q_valid, tid);
+  if constexpr (PREC) load_tile_async(sQl, p.Qlo + qoff, p.ldq, q_valid, tid);
+  if (n_tiles > 0) load_kv(0, 0);
   cp_async_commit();
 
   float o[8][4];
@@ -64,14 +79,12 @@ flash_attn_kernel(AttnCall p) {
   for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
   float m_i[2] = {-INFINITY, -INFINITY}, l_i[2] = {0.f, 0.f};
   const float sl2 = p.scale * 1.4426950408889634f;
-  uint32_t qf[4][4];
+  uint32_t qf[4][4], qfl[PREC ? 4 : 1][4];
 
   for (int kt = 0; kt < n_tiles; ++kt) {
     const int buf = kt & 1;
     if (kt + 1 < n_tiles) {
-      const int kn = (kt + 1) * FA_BK;
-      load_tile_async(sK[buf ^ 1], Kg + (size_t)kn * p.ldk, p.ldk, min(FA_BK, k_end - kn), tid);
-      load_tile_async(sV[buf ^ 1], Vg + (size_t)kn * p.ldv, p.ldv, min(FA_BK, k_end - kn), tid);
+      load_kv(buf ^ 1, (kt + 1) * FA_BK);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -85,6 +98,7 @@ flash_attn_kernel(AttnCall p) {
         const int row = warp * 16 + (lane & 15);
         const int chunk = kk * 2 + (lane >> 4);
         ldmatrix_x4(qf[kk], sQ + sw_off(row, chunk));
+        if constexpr (PREC) ldmatrix_x4(qfl[kk], sQl + sw_off(row, chunk));
       }
     }
     // ---- S = Q K^T (16 x 64 per warp)
@@ -98,9 +112,17 @@ flash_attn_kernel(AttnCall p) {
         uint32_t b[4];
         const int row = jp * 16 + (lane & 7) + ((lane >> 4) << 3);
         const int chunk = kk * 2 + ((lane >> 3) & 1);
-        ldmatrix_x4(b, sK[buf] + sw_off(row, chunk));
+        ldmatrix_x4(b, sK + buf * TILE + sw_off(row, chunk));
         mma_16816(s[2 * jp], qf[kk], b[0], b[1]);
         mma_16816(s[2 * jp + 1], qf[kk], b[2], b[3]);
+        if constexpr (PREC) {
+          mma_16816(s[2 * jp], qfl[kk], b[0], b[1]);
+          mma_16816(s[2 * jp + 1], qfl[kk], b[2], b[3]);
+          uint32_t bl[4];
+          ldmatrix_x4(bl, sKl + buf * TILE + sw_off(row, chunk));
+          mma_16816(s[2 * jp], qf[kk], bl[0], bl[1]);
+          mma_16816(s[2 * jp + 1], qf[kk], bl[2], bl[3]);
+        }
       }
     }
     // ---- mask + online softmax
@@ -148,19 +170,37 @@ flash_attn_kernel(AttnCall p) {
     // ---- O += P V
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step
-      uint32_t a[4];
+      uint32_t a[4], al[4];
       a[0] = pack_half2(s[2 * kk][0], s[2 * kk][1]);
       a[1] = pack_half2(s[2 * kk][2], s[2 * kk][3]);
       a[2] = pack_half2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
       a[3] = pack_half2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      if constexpr (PREC) {
+        auto lo2 = [](float x, float y, uint32_t hi) {
+          const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+          return pack_half2(x - h.x, y - h.y);
+        };
+        al[0] = lo2(s[2 * kk][0], s[2 * kk][1], a[0]);
+        al[1] = lo2(s[2 * kk][2], s[2 * kk][3], a[1]);
+        al[2] = lo2(s[2 * kk + 1][0], s[2 * kk + 1][1], a[2]);
+        al[3] = lo2(s[2 * kk + 1][2], s[2 * kk + 1][3], a[3]);
+      }
 #pragma unroll
       for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-wide output column tiles
         uint32_t b[4];
         const int row = kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
         const int chunk = jp * 2 + (lane >> 4);
-        ldmatrix_x4_trans(b, sV[buf] + sw_off(row, chunk));
+        ldmatrix_x4_trans(b, sV + buf * TILE + sw_off(row, chunk));
         mma_16816(o[2 * jp], a, b[0], b[1]);
         mma_16816(o[2 * jp + 1], a, b[2], b[3]);
+        if constexpr (PREC) {
+          mma_16816(o[2 * jp], al, b[0], b[1]);
+          mma_16816(o[2 * jp + 1], al, b[2], b[3]);
+          uint32_t bl[4];
+          ldmatrix_x4_trans(bl, sVl + buf * TILE + sw_off(row, chunk));
+          mma_16816(o[2 * jp], a, bl[0], bl[1]);
+          mma_16816(o[2 * jp + 1], a, bl[2], bl[3]);
+        }
       }
     }
     __syncthreads();
@@ -174,12 +214,19 @@ flash_attn_kernel(AttnCall p) {
   const float inv0 = l_i[0] > 0.f ? 1.f / l_i[0] : 0.f;
   const float inv1 = l_i[1] > 0.f ? 1.f / l_i[1] : 0.f;
   const int r0 = warp * 16 + g, r1 = r0 + 8;
-  __half* Og = p.O + (size_t)(p.q_start[seq] + q0) * p.ldo + head * HD;
+  const size_t ooff = (size_t)(p.q_start[seq] + q0) * p.ldo + head * HD;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int col = j * 8 + 2 * t;
-    if (r0 < q_valid) *reinterpret_cast<uint32_t*>(Og + (size_t)r0 * p.ldo + col) = pack_half2(o[j][0] * inv0, o[j][1] * inv0);
-    if (r1 < q_valid) *reinterpret_cast<uint32_t*>(Og + (size_t)r1 * p.ldo + col) = pack_half2(o[j][2] * inv1, o[j][3] * inv1);
+    const float v00 = o[j][0] * inv0, v01 = o[j][1] * inv0, v10 = o[j][2] * inv1, v11 = o[j][3] * inv1;
+    const uint32_t h0 = pack_half2(v00, v01), h1 = pack_half2(v10, v11);
+    if (r0 < q_valid) *reinterpret_cast<uint32_t*>(p.O + ooff + (size_t)r0 * p.ldo + col) = h0;
+    if (r1 < q_valid) *reinterpret_cast<uint32_t*>(p.O + ooff + (size_t)r1 * p.ldo + col) = h1;
+    if constexpr (PREC) {
+      const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+      if (r0 < q_valid) *reinterpret_cast<uint32_t*>(p.Olo + ooff + (size_t)r0 * p.ldo + col) = pack_half2(v00 - f0.x, v01 - f0.y);
+      if (r1 < q_valid) *reinterpret_cast<uint32_t*>(p.Olo + ooff + (size_t)r1 * p.ldo + col) = pack_half2(v10 - f1.x, v11 - f1.y);
+    }
   }
 }
 
@@ -187,7 +234,16 @@ int flash_attn(const AttnCall& c, cudaStream_t stream) {
   if (c.n_seqs <= 0 || c.max_q <= 0) return M5_OK;
   if ((c.ldq | c.ldk | c.ldv) % 8 != 0 || c.ldo % 2 != 0) return M5_ERR_ARG;
   dim3 grid((c.max_q + FA_BQ - 1) / FA_BQ, c.n_heads, c.n_seqs);
-  flash_attn_kernel<<<grid, FA_THREADS, 0, stream>>>(c);
+  const bool prec = c.Qlo != nullptr;
+  if (prec && (!c.Klo || !c.Vlo || !c.Olo)) return M5_ERR_ARG;
+  const size_t smem = (size_t)(prec ? 10 : 5) * FA_BQ * HD * sizeof(__half);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(flash_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 10 * FA_BQ * HD * 2);
+    attr_set = true;
+  }
+  if (prec) flash_attn_kernel<true><<<grid, FA_THREADS, smem, stream>>>(c);
+  else flash_attn_kernel<false><<<grid, FA_THREADS, smem, stream>>>(c);
   return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
 }
 
@@ -198,7 +254,12 @@ int flash_attn(const AttnCall& c, cudaStream_t stream) {
 // keeps 4 such instructions in flight for K and for V; partial (max, sum, acc[64]) per split are merged by a second
 // kernel in a fixed order (deterministic).
 static constexpr int DA_THREADS = 128;
-static constexpr int DA_KEYS = 128;   // keys per CTA
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {  // the KV cache is read once per step: keep it out of L1
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+static constexpr int DA_KEYS = 256;   // keys per CTA
 
 __global__ void __launch_bounds__(DA_THREADS)
 decode_attn_split_kernel(DecodeAttnCall p) {
@@ -230,8 +291,8 @@ decode_attn_split_kernel(DecodeAttnCall p) {
     for (int u = 0; u < 4; ++u) {
       const int key = kbase + u * 4 + grp;
       if (key < k1) {
-        kv[u] = *reinterpret_cast<const uint4*>(kb + (size_t)key * D);
-        vv[u] = *reinterpret_cast<const uint4*>(vb + (size_t)key * D);
+        kv[u] = ldg_stream16(kb + (size_t)key * D);
+        vv[u] = ldg_stream16(vb + (size_t)key * D);
       } else {
         kv[u] = make_uint4(0, 0, 0, 0);
         vv[u] = make_uint4(0, 0, 0, 0);

@@ -144,7 +144,9 @@ static void pick_split(int N, int K, int num_sms, int& kslice, int& ksplit) {
   int best = 1;
   for (int s = 1; s <= kb; ++s) {
     if (kb % s) continue;
-    if ((long)tiles * s <= 2L * num_sms && (kb / s) * 64 <= 2048) best = s;
+    // fill about two CTAs per SM, but keep slices >= 256 columns and at most 8 of them (the last CTA of a row tile
+    // adds the slices serially)
+    if ((long)tiles * s <= 2L * num_sms && s <= 8 && (kb / s) * 64 >= 256) best = s;
   }
   while ((K / best) > 2048 && best < kb) {  // shared-memory bound on the activation slice
     ++best;

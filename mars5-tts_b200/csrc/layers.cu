@@ -57,15 +57,17 @@ int load_dec_layer(m5_ctx* ctx, const std::string& prefix, DecLayerW& w) {
 
 static size_t al(size_t n) { return (n + 255) & ~size_t(255); }
 size_t block_scratch_bytes(int rows, int mem_rows, int D, int ff) {
-  return al((size_t)rows * 2 * D * 2) + al((size_t)rows * 3 * D * 2) + al((size_t)rows * D * 2) +
-         al((size_t)rows * 2 * ff * 2) + al((size_t)mem_rows * 2 * D * 2) + 4096;
+  return al((size_t)rows * 2 * D * 2) + 2 * al((size_t)rows * 3 * D * 2) + al((size_t)rows * 2 * D * 2) +
+         al((size_t)rows * 2 * ff * 2) + 2 * al((size_t)mem_rows * 2 * D * 2) + 8192;
 }
 void block_scratch_carve(Arena& a, BlockScratch& s, int rows, int mem_rows, int D, int ff) {
   s.h16 = a.get<__half>((size_t)rows * 2 * D);
   s.qkv16 = a.get<__half>((size_t)rows * 3 * D);
-  s.att16 = a.get<__half>((size_t)rows * D);
+  s.qkv16_lo = a.get<__half>((size_t)rows * 3 * D);
+  s.att16 = a.get<__half>((size_t)rows * 2 * D);
   s.g16 = a.get<__half>((size_t)rows * 2 * ff);
   s.kv16 = mem_rows > 0 ? a.get<__half>((size_t)mem_rows * 2 * D) : nullptr;
+  s.kv16_lo = mem_rows > 0 ? a.get<__half>((size_t)mem_rows * 2 * D) : nullptr;
 }
 
 // h16 <- LayerNorm(x) as fp16 (hi | lo halves side by side when precise)
@@ -99,23 +101,48 @@ static int ffn_block(m5_ctx* ctx, float* x, int rows, int D, int ff, const float
   return M5_OK;
 }
 
+// x += out_proj(softmax(q k^T / 8) v): shared by self- and cross-attention.  Queries come from h16 (already normalised),
+// keys/values either from the same projection (kv_src == nullptr) or from the encoder memory.
+static int attn_block(m5_ctx* ctx, float* x, const SeqSet& seqs, int D, int H, bool precise, const BlockScratch& s,
+                      const __half* in_w, const float* in_b, const __half* out_w, const float* out_b,
+                      const __half* mem16, const SeqSet* mem_seqs, const __half* kv_w, const float* kv_b) {
+  const int rows = seqs.rows;
+  const bool cross = mem16 != nullptr;
+  const int qn = cross ? D : 3 * D;  // width of the projection of h16
+  GemmCall gq = lin(s.h16, rows, D, precise, in_w, qn, in_b);
+  gq.out = s.qkv16; gq.ldc = qn; gq.mode = precise ? M5_OUT_F16_SPLIT : M5_OUT_F16; gq.out_lo = precise ? s.qkv16_lo : nullptr;
+  M5_TRY(run_gemm(ctx, gq));
+  AttnCall a;
+  a.Q = s.qkv16; a.ldq = qn; a.Qlo = precise ? s.qkv16_lo : nullptr;
+  if (cross) {
+    GemmCall gkv = lin(mem16, mem_seqs->rows, D, precise, kv_w, 2 * D, kv_b);
+    gkv.out = s.kv16; gkv.ldc = 2 * D; gkv.mode = precise ? M5_OUT_F16_SPLIT : M5_OUT_F16; gkv.out_lo = precise ? s.kv16_lo : nullptr;
+    M5_TRY(run_gemm(ctx, gkv));
+    a.K = s.kv16; a.V = s.kv16 + D; a.ldk = a.ldv = 2 * D;
+    if (precise) { a.Klo = s.kv16_lo; a.Vlo = s.kv16_lo + D; }
+    a.k_start = mem_seqs->start; a.k_len = mem_seqs->len; a.k_rows = mem_seqs->rows;
+    a.flops_hint = 256.0 * H * seqs.cross_pairs;
+  } else {
+    a.K = s.qkv16 + D; a.V = s.qkv16 + 2 * D; a.ldk = a.ldv = 3 * D;
+    if (precise) { a.Klo = s.qkv16_lo + D; a.Vlo = s.qkv16_lo + 2 * D; }
+    a.k_start = seqs.start; a.k_len = seqs.klen ? seqs.klen : seqs.len; a.k_rows = rows;
+    a.flops_hint = 256.0 * H * seqs.self_pairs;
+  }
+  a.O = s.att16; a.ldo = precise ? 2 * D : D; a.Olo = precise ? s.att16 + D : nullptr;
+  a.n_heads = H; a.n_seqs = seqs.n; a.max_q = seqs.max_len; a.q_start = seqs.start; a.q_len = seqs.len; a.q_rows = rows;
+  if (precise) a.impl = 1;  // the split-precision path lives in the mma.sync kernel
+  M5_TRY(run_attn(ctx, a));
+  GemmCall go = lin(s.att16, rows, D, precise, out_w, D, out_b);
+  go.out = x; go.ldc = D; go.mode = M5_OUT_F32; go.accumulate = 1;
+  return run_gemm(ctx, go);
+}
+
 int encoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const EncLayerW& w, int D, int H, int ff, float eps,
                   bool precise, const BlockScratch& s) {
   const int rows = seqs.rows;
   // x = x + out_proj(MHA(LN1(x)))
   M5_TRY(ln_to_f16(ctx, x, rows, D, w.n1w, w.n1b, eps, precise, s.h16));
-  GemmCall gq = lin(s.h16, rows, D, precise, w.in_w, 3 * D, w.in_b);
-  gq.out = s.qkv16; gq.ldc = 3 * D; gq.mode = M5_OUT_F16;
-  M5_TRY(run_gemm(ctx, gq));
-  AttnCall a;
-  a.Q = s.qkv16; a.K = s.qkv16 + D; a.V = s.qkv16 + 2 * D; a.ldq = a.ldk = a.ldv = 3 * D;
-  a.O = s.att16; a.ldo = D; a.n_heads = H; a.n_seqs = seqs.n; a.max_q = seqs.max_len;
-  a.q_start = seqs.start; a.q_len = seqs.len; a.k_start = seqs.start; a.k_len = seqs.klen ? seqs.klen : seqs.len;
-  a.flops_hint = 256.0 * H * seqs.self_pairs; a.q_rows = rows; a.k_rows = rows;
-  M5_TRY(run_attn(ctx, a));
-  GemmCall go = lin(s.att16, rows, D, false, w.out_w, D, w.out_b);
-  go.out = x; go.ldc = D; go.mode = M5_OUT_F32; go.accumulate = 1;
-  M5_TRY(run_gemm(ctx, go));
+  M5_TRY(attn_block(ctx, x, seqs, D, H, precise, s, w.in_w, w.in_b, w.out_w, w.out_b, nullptr, nullptr, nullptr, nullptr));
   // x = x + linear2(swiglu(LN2(x)))
   return ffn_block(ctx, x, rows, D, ff, w.n2w, w.n2b, eps, w.wv, w.w2, w.b2, precise, s);
 }
@@ -123,37 +150,10 @@ int encoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const EncLayerW& w,
 int decoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const __half* mem16, const SeqSet& mem_seqs,
                   const DecLayerW& w, int D, int H, int ff, float eps, bool precise, const BlockScratch& s) {
   const int rows = seqs.rows;
-  // self attention
   M5_TRY(ln_to_f16(ctx, x, rows, D, w.n1w, w.n1b, eps, precise, s.h16));
-  GemmCall gq = lin(s.h16, rows, D, precise, w.sa_in_w, 3 * D, w.sa_in_b);
-  gq.out = s.qkv16; gq.ldc = 3 * D; gq.mode = M5_OUT_F16;
-  M5_TRY(run_gemm(ctx, gq));
-  AttnCall a;
-  a.Q = s.qkv16; a.K = s.qkv16 + D; a.V = s.qkv16 + 2 * D; a.ldq = a.ldk = a.ldv = 3 * D;
-  a.O = s.att16; a.ldo = D; a.n_heads = H; a.n_seqs = seqs.n; a.max_q = seqs.max_len;
-  a.q_start = seqs.start; a.q_len = seqs.len; a.k_start = seqs.start; a.k_len = seqs.len;
-  a.flops_hint = 256.0 * H * seqs.self_pairs; a.q_rows = rows; a.k_rows = rows;
-  M5_TRY(run_attn(ctx, a));
-  GemmCall go = lin(s.att16, rows, D, false, w.sa_out_w, D, w.sa_out_b);
-  go.out = x; go.ldc = D; go.mode = M5_OUT_F32; go.accumulate = 1;
-  M5_TRY(run_gemm(ctx, go));
-  // cross attention over the encoder memory
+  M5_TRY(attn_block(ctx, x, seqs, D, H, precise, s, w.sa_in_w, w.sa_in_b, w.sa_out_w, w.sa_out_b, nullptr, nullptr, nullptr, nullptr));
   M5_TRY(ln_to_f16(ctx, x, rows, D, w.n2w, w.n2b, eps, precise, s.h16));
-  GemmCall gcq = lin(s.h16, rows, D, precise, w.ca_q_w, D, w.ca_q_b);
-  gcq.out = s.qkv16; gcq.ldc = D; gcq.mode = M5_OUT_F16;
-  M5_TRY(run_gemm(ctx, gcq));
-  GemmCall gkv = lin(mem16, mem_seqs.rows, D, precise, w.ca_kv_w, 2 * D, w.ca_kv_b);
-  gkv.out = s.kv16; gkv.ldc = 2 * D; gkv.mode = M5_OUT_F16;
-  M5_TRY(run_gemm(ctx, gkv));
-  AttnCall c;
-  c.Q = s.qkv16; c.ldq = D; c.K = s.kv16; c.V = s.kv16 + D; c.ldk = c.ldv = 2 * D;
-  c.O = s.att16; c.ldo = D; c.n_heads = H; c.n_seqs = seqs.n; c.max_q = seqs.max_len;
-  c.q_start = seqs.start; c.q_len = seqs.len; c.k_start = mem_seqs.start; c.k_len = mem_seqs.len;
-  c.flops_hint = 256.0 * H * seqs.cross_pairs; c.q_rows = rows; c.k_rows = mem_seqs.rows;
-  M5_TRY(run_attn(ctx, c));
-  GemmCall gco = lin(s.att16, rows, D, false, w.ca_out_w, D, w.ca_out_b);
-  gco.out = x; gco.ldc = D; gco.mode = M5_OUT_F32; gco.accumulate = 1;
-  M5_TRY(run_gemm(ctx, gco));
+  M5_TRY(attn_block(ctx, x, seqs, D, H, precise, s, w.ca_q_w, w.ca_q_b, w.ca_out_w, w.ca_out_b, mem16, &mem_seqs, w.ca_kv_w, w.ca_kv_b));
   return ffn_block(ctx, x, rows, D, ff, w.n3w, w.n3b, eps, w.wv, w.w2, w.b2, precise, s);
 }
 

@@ -43,9 +43,11 @@ int load_dec_layer(m5_ctx* ctx, const std::string& prefix, DecLayerW& w);
 struct BlockScratch {
   __half* h16 = nullptr;    // [rows, 2*D]   normalised activations (hi | lo when precise)
   __half* qkv16 = nullptr;  // [rows, 3*D]
-  __half* att16 = nullptr;  // [rows, D]
+  __half* att16 = nullptr;  // [rows, 2*D]   attention output (hi | lo when precise)
   __half* g16 = nullptr;    // [rows, 2*ff]  gated activations (hi | lo when precise)
   __half* kv16 = nullptr;   // [mem_rows, 2*D] cross-attention keys/values
+  __half* qkv16_lo = nullptr;  // [rows, 3*D]     low halves of q/k/v (precise mode)
+  __half* kv16_lo = nullptr;   // [mem_rows, 2*D]
 };
 size_t block_scratch_bytes(int rows, int mem_rows, int D, int ff);
 void block_scratch_carve(Arena& a, BlockScratch& s, int rows, int mem_rows, int D, int ff);

@@ -79,6 +79,8 @@ struct AttnCall {
   double flops_hint = 0.0;  // 4 * 64 * heads * sum_s(q_len*k_len) (halved when causal); profiling only
   int q_rows = 0, k_rows = 0;  // total rows of the Q and K/V buffers (TMA bounds); required by the tcgen05 kernel
   int impl = 0;                // 0 auto, 1 mma.sync kernel, 2 tcgen05 kernel
+  // split-precision mode (mma.sync kernel only): low halves of Q/K/V (same strides) and of the output
+  const __half* Qlo = nullptr; const __half* Klo = nullptr; const __half* Vlo = nullptr; __half* Olo = nullptr;
 };
 int flash_attn(const AttnCall& c, cudaStream_t stream);      // mma.sync (causal prefill, tiny problems)
 int flash_attn_tc5(const AttnCall& c, cudaStream_t stream);  // tcgen05 / TMEM (attention_tc5.cu)

@@ -198,7 +198,8 @@ def test_nar_forward_logits(tiny, precise):
         got = eng.nar_forward([inp["nar_c_text"].numpy()], [inp["nar_c_codes"].numpy()], [inp["nar_x"].numpy()], t,
                               drop_cond=drop, precise=bool(precise))[0]
         err = np.abs(got - GOLD[key]).max()
-        assert err < logit_tol(GOLD[key], 3e-4 if precise else 1e-3), (key, err)
+        # precise mode (split-fp16 operands in GEMMs and attention) must meet the north_star bound in absolute terms
+        assert err < (1e-3 if precise else logit_tol(GOLD[key])), (key, err)
 
 
 def test_nar_forward_batch_varlen(tiny):
