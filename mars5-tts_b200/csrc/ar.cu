@@ -10,10 +10,13 @@
 //                      sampler).  All per-row state (ids, lengths, done flags) lives on the device; the host only polls
 //                      an "all rows done" counter every cfg.sync_every steps.
 // Numerics mirror the reference's GPU path (fp16 GEMM operands / fp16 KV cache / fp32 residual stream).
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
 #include "layers.h"
+#include "ptx.cuh"
 #include "sampler.h"
 
 namespace m5 {
@@ -92,6 +95,8 @@ __global__ void ar_init_state_kernel(const int* prompt, const int* p_off, const 
 // Embedding of the most recent token of every row -> x [B, D] fp32 (nn.Embedding is not autocast: fp32 value of the
 // fp16-exact weight).
 __global__ void ar_embed_last_kernel(const int* ids, int stride, const int* tok_len, const __half* table, int D, float* x) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int tok = ids[(size_t)b * stride + tok_len[b] - 1];
   for (int c = threadIdx.x; c < D; c += blockDim.x) x[(size_t)b * D + c] = __half2float(table[(size_t)tok * D + c]);
@@ -238,7 +243,8 @@ static int ar_decode_step(m5_ctx* ctx, const ArWeights& w, int B, const ArState&
   const m5_model_cfg& c = ctx->cfg;
   const int D = c.ar_dim, F = c.ar_hidden, V = c.ar_vocab;
   const size_t layer_stride = (size_t)B * Wc * D;
-  ar_embed_last_kernel<<<B, 256, 0, ctx->stream>>>(st.ids, sc.hist_stride, st.tok_len, w.embed, D, st.x);
+  if (launch_k(ar_embed_last_kernel, dim3(B), dim3(256), 0, ctx->stream, (const int*)st.ids, sc.hist_stride, (const int*)st.tok_len, w.embed, D, st.x) != cudaSuccess)
+    return ctx->fail(M5_ERR_CUDA, "ar_embed_last launch failed");
   ctx->launches++;
   for (int l = 0; l < c.ar_layers; ++l) {
     const ArLayerW& lw = w.layers[l];
@@ -435,7 +441,10 @@ int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int3
   if (max_steps > 0) {
     const int64_t before = ctx->launches;
     M5_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    static const bool no_pdl = getenv("M5_DISABLE_PDL") != nullptr;
+    g_use_pdl = !no_pdl;  // kernels of the step overlap their prologues (weight prefetch) with their predecessor's tail
     int rc = ar_decode_step(ctx, w, B, st, kc, vc, Wc, sc);
+    g_use_pdl = false;
     cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
     step_launches = ctx->launches - before;
     ctx->launches = before;

@@ -263,6 +263,8 @@ static constexpr int DA_KEYS = 256;   // keys per CTA
 
 __global__ void __launch_bounds__(DA_THREADS)
 decode_attn_split_kernel(DecodeAttnCall p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   if (p.done && p.done[b]) return;
   const int L = p.kv_len[b];
@@ -351,6 +353,8 @@ decode_attn_split_kernel(DecodeAttnCall p) {
 }
 
 __global__ void decode_attn_merge_kernel(DecodeAttnCall p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;  // 32 threads
   if (p.done && p.done[b]) return;
   const float* sp = p.scratch + ((size_t)(b * p.H + h) * p.n_split) * (HD + 2);
@@ -376,10 +380,9 @@ int decode_attn_splits_for(int max_kv) { return (max_kv + DA_KEYS - 1) / DA_KEYS
 int decode_attn(const DecodeAttnCall& c, cudaStream_t stream) {
   if (c.B <= 0) return M5_OK;
   dim3 grid(c.n_split, c.H, c.B);
-  decode_attn_split_kernel<<<grid, DA_THREADS, 0, stream>>>(c);
+  if (launch_k(decode_attn_split_kernel, grid, dim3(DA_THREADS), 0, stream, c) != cudaSuccess) return M5_ERR_CUDA;
   dim3 g2(c.H, c.B);
-  decode_attn_merge_kernel<<<g2, 32, 0, stream>>>(c);
-  return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
+  return launch_k(decode_attn_merge_kernel, g2, dim3(32), 0, stream, c) == cudaSuccess ? M5_OK : M5_ERR_CUDA;
 }
 
 }  // namespace m5

@@ -11,6 +11,8 @@
 
 namespace m5 {
 
+bool g_use_pdl = false;  // set only while the AR decode step is being captured into its CUDA graph
+
 int Arena::reserve(size_t bytes) {
   c->arena_off = 0;
   if (bytes <= c->arena_cap) return M5_OK;

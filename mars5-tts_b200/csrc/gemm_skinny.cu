@@ -45,15 +45,7 @@ gemm_skinny_kernel(SkinnyCall p, int kslice, int ksplit) {
   const int xstride = kslice * 2 + 64;  // bytes; kslice % 64 == 0 -> stride == 64 (mod 128)
   constexpr int BT = 8 * NT;
 
-  // stage X[:, kbase : kbase + kslice] (rows >= B are zero-filled) -- asynchronous
-  const int vec_per_row = kslice / 8;
-  for (int i = tid; i < BT * vec_per_row; i += SK_THREADS) {
-    const int row = i / vec_per_row, v = i - row * vec_per_row;
-    const bool ok = row < p.B;
-    cp_async16(sk_smem + (size_t)row * xstride + v * 16, ok ? (p.X + (size_t)row * p.K + kbase + v * 8) : p.X, ok);
-  }
-  cp_async_commit();
-
+  pdl_launch_dependents();
   float acc[NT][4];
 #pragma unroll
   for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
@@ -62,18 +54,37 @@ gemm_skinny_kernel(SkinnyCall p, int kslice, int ksplit) {
   const __half* w1 = p.W + (size_t)r1 * p.K + kbase + 8 * t;
   const int chunks = kslice / 32;
 
-  for (int c0 = 0; c0 < chunks; c0 += SK_UNROLL) {
-    uint4 wa[SK_UNROLL], wb[SK_UNROLL];
+  // The weights do not depend on the previous kernel: the first batch is requested BEFORE the grid dependency is
+  // waited for, i.e. while the producer of X may still be running (programmatic dependent launch).
+  uint4 wa[SK_UNROLL], wb[SK_UNROLL];
 #pragma unroll
-    for (int u = 0; u < SK_UNROLL; ++u) {
-      if (c0 + u < chunks) {
-        wa[u] = ldg_stream(w0 + (c0 + u) * 32);
-        wb[u] = ldg_stream(w1 + (c0 + u) * 32);
-      }
+  for (int u = 0; u < SK_UNROLL; ++u) {
+    if (u < chunks) {
+      wa[u] = ldg_stream(w0 + u * 32);
+      wb[u] = ldg_stream(w1 + u * 32);
     }
-    if (c0 == 0) {  // the weight loads above are already in flight while the activation slice lands
-      cp_async_wait<0>();
-      __syncthreads();
+  }
+  pdl_wait();
+  // stage X[:, kbase : kbase + kslice] (rows >= B are zero-filled)
+  const int vec_per_row = kslice / 8;
+  for (int i = tid; i < BT * vec_per_row; i += SK_THREADS) {
+    const int row = i / vec_per_row, v = i - row * vec_per_row;
+    const bool ok = row < p.B;
+    cp_async16(sk_smem + (size_t)row * xstride + v * 16, ok ? (p.X + (size_t)row * p.K + kbase + v * 8) : p.X, ok);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+
+  for (int c0 = 0; c0 < chunks; c0 += SK_UNROLL) {
+    if (c0 > 0) {
+#pragma unroll
+      for (int u = 0; u < SK_UNROLL; ++u) {
+        if (c0 + u < chunks) {
+          wa[u] = ldg_stream(w0 + (c0 + u) * 32);
+          wb[u] = ldg_stream(w1 + (c0 + u) * 32);
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < SK_UNROLL; ++u) {
@@ -175,10 +186,11 @@ int gemm_skinny(const SkinnyCall& c, cudaStream_t stream, int num_sms) {
     attr_set = true;
   }
   const int grid = tiles * ksplit;
-  if (NT == 1) gemm_skinny_kernel<1><<<grid, SK_THREADS, smem, stream>>>(c, kslice, ksplit);
-  else if (NT == 2) gemm_skinny_kernel<2><<<grid, SK_THREADS, smem, stream>>>(c, kslice, ksplit);
-  else gemm_skinny_kernel<4><<<grid, SK_THREADS, smem, stream>>>(c, kslice, ksplit);
-  return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
+  cudaError_t e;
+  if (NT == 1) e = launch_k(gemm_skinny_kernel<1>, dim3(grid), dim3(SK_THREADS), smem, stream, c, kslice, ksplit);
+  else if (NT == 2) e = launch_k(gemm_skinny_kernel<2>, dim3(grid), dim3(SK_THREADS), smem, stream, c, kslice, ksplit);
+  else e = launch_k(gemm_skinny_kernel<4>, dim3(grid), dim3(SK_THREADS), smem, stream, c, kslice, ksplit);
+  return e == cudaSuccess ? M5_OK : M5_ERR_CUDA;
 }
 
 }  // namespace m5

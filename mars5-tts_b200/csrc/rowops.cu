@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(256) norm_rows_kernel(NormCall p) {
 
 // Few rows (AR decode: M = batch): one CTA per row so that the whole row is in flight at once (latency-bound case).
 __global__ void __launch_bounds__(256) norm_row_cta_kernel(NormCall p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x, tid = threadIdx.x;
   const int src = p.row_map ? p.row_map[row] : row;
   const float* x = p.x + (size_t)src * p.ldx;
@@ -136,8 +138,7 @@ int norm_rows(const NormCall& c, cudaStream_t stream) {
   if (c.M <= 0) return M5_OK;
   if (c.D % 4 != 0 || c.ldx % 4 != 0 || c.ldo % 4 != 0) return M5_ERR_ARG;
   if (c.M <= 64 && c.D <= 2048) {
-    norm_row_cta_kernel<<<c.M, 256, 0, stream>>>(c);
-    return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
+    return launch_k(norm_row_cta_kernel, dim3(c.M), dim3(256), 0, stream, c) == cudaSuccess ? M5_OK : M5_ERR_CUDA;
   }
   const int wpb = 8;
   norm_rows_kernel<<<(c.M + wpb - 1) / wpb, wpb * 32, 0, stream>>>(c);
@@ -213,6 +214,8 @@ int rope_kv(__half* qkv, int ld, int n_rows, int H, const int* row_seq, const in
 // rotate, write q as fp16 [B, D] and append k, v at position pos[b] = len[b] - 1.
 __global__ void rope_kv_decode_kernel(const float* qkv, int B, int H, const int* len, __half* qout, __half* kc,
                                       __half* vc, int W, const float* inv_freq, const int* active) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int D = H * 64, pairs = D / 2;
   const int total = B * pairs;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -234,8 +237,7 @@ __global__ void rope_kv_decode_kernel(const float* qkv, int B, int H, const int*
 int rope_kv_decode(const float* qkv, int B, int H, const int* len, __half* qout, __half* kc, __half* vc, int W,
                    const float* inv_freq, const int* active, cudaStream_t stream) {
   const int total = B * H * 32;
-  rope_kv_decode_kernel<<<(total + 255) / 256, 256, 0, stream>>>(qkv, B, H, len, qout, kc, vc, W, inv_freq, active);
-  return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
+  return launch_k(rope_kv_decode_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, qkv, B, H, len, qout, kc, vc, W, inv_freq, active) == cudaSuccess ? M5_OK : M5_ERR_CUDA;
 }
 
 // ------------------------------------------------------------------------------------------------ embeddings

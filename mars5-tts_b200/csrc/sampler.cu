@@ -34,6 +34,8 @@ __device__ float philox_uniform(uint64_t seed, uint64_t stream, uint32_t step, u
 static constexpr int SP_THREADS = 256;
 
 __global__ void __launch_bounds__(SP_THREADS) ar_sample_kernel(SampleCall p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t sp_smem[];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int V = p.V;
@@ -275,8 +277,7 @@ int ar_sample(SampleCall& c, cudaStream_t stream) {
       return M5_ERR_CUDA;
     configured = smem;
   }
-  ar_sample_kernel<<<c.B, SP_THREADS, smem, stream>>>(c);
-  return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
+  return launch_k(ar_sample_kernel, dim3(c.B), dim3(SP_THREADS), smem, stream, c) == cudaSuccess ? M5_OK : M5_ERR_CUDA;
 }
 
 }  // namespace m5
