@@ -2,17 +2,27 @@
 // softmax(Q K^T / 8) V over packed variable-length sequences, head_dim 64 (reference: nn.MultiheadAttention inside
 // nn.TransformerEncoder/DecoderLayer, mars5/model.py:179-204,339-341).
 //
-// One CTA = 128 queries of one (sequence, head); keys/values stream in tiles of 128.
-//   warp 0     TMA producer: Q once, then K_j / V_j tiles (cp.async.bulk.tensor, 128B swizzle) into single buffers that
-//              are refilled as soon as the MMA that read them has committed
-//   warp 1     MMA issuer:  S_j = Q K_j^T   (UMMA 128x128x16, both operands K-major)         -> TMEM cols [0,128)
-//                           O_j = P_j V_j   (UMMA 128x64x16, A = P_j in smem, B = V_j MN-major) -> TMEM cols [128,192)
-//   warps 2-5  softmax, one query row per thread: two passes over S_j in TMEM (row max, then exp2 / row sum), P_j written
-//              to shared memory as fp16 in the K-major 128B-swizzle layout the UMMA A-descriptor expects; O_j is read
-//              back from TMEM and accumulated in registers with the usual online-softmax rescale (no TMEM read-modify-
-//              write); final O / l is stored as fp16.
-// 80 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM, so one CTA's exponentials overlap the other's
-// MMAs without an intra-CTA ping-pong.
+// One CTA = 128 queries of one (sequence, head); keys/values stream in tiles of 64.
+//   warp 0     TMA producer: Q once, then K_j / V_j tiles (cp.async.bulk.tensor, 128B swizzle) into a 4-deep K ring and
+//              a 3-deep V ring; K runs two tiles ahead of V
+//   warp 1     MMA issuer:  S_j = Q K_j^T   (UMMA 128x64x16, both operands K-major)  -> TMEM score slot j % 3
+//                           O  += P_j V_j   (UMMA 128x64x16, A = P_j in smem, B = V_j MN-major) -> TMEM columns 192..255
+//              S_{j+2} is issued before PV_j, so the scores of the next two tiles are computed while the softmax warps
+//              still work on tile j: the S -> softmax -> P -> PV chain of a CTA has no tensor-core round trip in it
+//   warps 2-5  softmax, one query row per thread, ONE pass over S_j ("lazy" reference point):
+//              * O stays resident in TMEM for the whole key loop (PV accumulates in place);
+//              * a tile is exponentiated against the row maximum already in use while its own maximum is tracked on the
+//                side; only when some row of the warp grew by more than 2^8 (or on the first tile) is the exact path
+//                taken: row maximum first, then O (tcgen05.ld -> mul -> tcgen05.st) and l are moved to the new
+//                reference point.  P <= 2^8 fits fp16 and O / l does not depend on the reference point, so the result
+//                is the same softmax(QK^T/8) V;
+//              * sums and maxima use independent accumulators (3-input max), P_j is written to shared memory as fp16 in
+//                the K-major 128B-swizzle layout the UMMA A-descriptor expects (double buffered).
+// 104 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM.
+//
+// History (profiles/README.md): the first version (128-key tiles, two passes over S, O folded into registers every
+// tile) ran at 413 TFLOP/s on the NAR shape; one-pass lazy softmax with O in TMEM 551; S issued ahead of PV 620; this
+// 64-key ring 610 with the tensor round trip gone -- what is left is per-tile instruction overhead and MUFU.EX2.
 #include <cuda.h>
 
 #include "m5_internal.h"
@@ -20,14 +30,20 @@
 
 namespace m5 {
 
-static constexpr int AT_BQ = 128, AT_BK = 128, AT_HD = 64, AT_THREADS = 192;
+static constexpr int AT_BQ = 128, AT_BK = 64, AT_HD = 64, AT_THREADS = 192;
+static constexpr int AT_KST = 4, AT_VST = 3, AT_KLEAD = 2, AT_SST = 3;   // K ring, V ring, K lead over V, S slots
 static constexpr int AT_Q_BYTES = AT_BQ * AT_HD * 2;     // 16 KB
-static constexpr int AT_K_BYTES = AT_BK * AT_HD * 2;     // 16 KB
-static constexpr int AT_V_BYTES = AT_BK * AT_HD * 2;     // 16 KB
-static constexpr int AT_P_BYTES = AT_BQ * AT_BK * 2;     // 32 KB (two 128x64 K-major blocks)
-static constexpr int AT_OFF_Q = 0, AT_OFF_K = AT_Q_BYTES, AT_OFF_V = AT_OFF_K + AT_K_BYTES, AT_OFF_P = AT_OFF_V + AT_V_BYTES;
-static constexpr int AT_OFF_BAR = AT_OFF_P + AT_P_BYTES;
-static constexpr int AT_SMEM = AT_OFF_BAR + 128 + 1024;
+static constexpr int AT_KV_BYTES = AT_BK * AT_HD * 2;    //  8 KB
+static constexpr int AT_P_BYTES = AT_BQ * AT_BK * 2;     // 16 KB (one 128-row K-major block)
+static constexpr int AT_OFF_Q = 0, AT_OFF_K = AT_Q_BYTES, AT_OFF_V = AT_OFF_K + AT_KST * AT_KV_BYTES,
+                     AT_OFF_P = AT_OFF_V + AT_VST * AT_KV_BYTES, AT_OFF_BAR = AT_OFF_P + 2 * AT_P_BYTES;
+static constexpr int AT_SMEM = AT_OFF_BAR + 256 + 1024;
+static constexpr int AT_TMEM_COLS = 256, AT_TMEM_O = AT_SST * AT_BK;   // S slots at 0/64/128, O at 192
+// mbarrier slots
+static constexpr int B_QFULL = 0, B_KFULL = 1, B_KFREE = B_KFULL + AT_KST, B_VFULL = B_KFREE + AT_KST, B_VFREE = B_VFULL + AT_VST,
+                     B_SREADY = B_VFREE + AT_VST, B_PREADY = B_SREADY + AT_SST, B_PVDONE = B_PREADY + 2, B_COUNT = B_PVDONE + 2;
+static_assert(B_COUNT * 8 + 8 <= 256, "barrier block");
+static_assert(AT_TMEM_O + AT_HD <= AT_TMEM_COLS, "TMEM budget");
 
 // Instruction descriptor: fp16 x fp16 -> fp32, A K-major, B major selectable.
 __host__ __device__ constexpr uint32_t at_idesc(uint32_t M, uint32_t N, uint32_t b_mn_major) {
@@ -50,11 +66,72 @@ M5_DEVINL float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+M5_DEVINL float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 
 struct AttnTc5Params {
   const int* q_start; const int* q_len; const int* k_start; const int* k_len;
   __half* O; int ldo;
   float scale_log2;
+};
+
+// 32 score columns of this thread's row -> P (fp16, swizzled smem), partial row sums, running tile maximum.
+// FULL = no key of the chunk is beyond the sequence (every tile but possibly the last).
+template <bool FULL>
+M5_DEVINL void softmax_chunk(const uint32_t (&r)[32], int c, int kvalid, float scale, float m_used, float (&rs)[4],
+                             float (&tm)[2], uint8_t* sp, int row) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const int q = i >> 1;
+    float s0 = __uint_as_float(r[i]), s1 = __uint_as_float(r[i + 1]);
+    float p0 = ex2_approx(fmaf(s0, scale, -m_used));
+    float p1 = ex2_approx(fmaf(s1, scale, -m_used));
+    if (!FULL) {
+      if (c * 32 + i >= kvalid) { p0 = 0.f; s0 = -INFINITY; }
+      if (c * 32 + i + 1 >= kvalid) { p1 = 0.f; s1 = -INFINITY; }
+    }
+    rs[q & 3] += p0 + p1;
+    tm[q & 1] = fmax3(tm[q & 1], s0, s1);
+    pk[q] = pack_half2(p0, p1);
+  }
+  // 32 columns = 4 chunks of 16 bytes of the 128-byte row; 16-byte chunk index XOR (row & 7) = 128B swizzle
+  uint8_t* blk = sp + row * 128;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int chunk = (c * 4 + q) ^ (row & 7);
+    *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  }
+}
+
+template <bool FULL>
+M5_DEVINL float chunk_max(const uint32_t (&r)[32], int c, int kvalid, float a) {
+  float b = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    float s0 = __uint_as_float(r[i]), s1 = __uint_as_float(r[i + 1]), s2 = __uint_as_float(r[i + 2]), s3 = __uint_as_float(r[i + 3]);
+    if (!FULL) {
+      if (c * 32 + i >= kvalid) s0 = -INFINITY;
+      if (c * 32 + i + 1 >= kvalid) s1 = -INFINITY;
+      if (c * 32 + i + 2 >= kvalid) s2 = -INFINITY;
+      if (c * 32 + i + 3 >= kvalid) s3 = -INFINITY;
+    }
+    a = fmax3(a, s0, s1);
+    b = fmax3(b, s2, s3);
+  }
+  return fmaxf(a, b);
+}
+
+// ring position that advances by one tile without integer division
+struct Ring {
+  int slot = 0;
+  uint32_t phase = 0;
+  M5_DEVINL void next(int depth) {
+    if (++slot == depth) { slot = 0; phase ^= 1u; }
+  }
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 2)
@@ -67,71 +144,81 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   extern __shared__ uint8_t at_smem_raw[];
   uint8_t* smem = at_smem_raw + ((1024u - (smem_u32(at_smem_raw) & 1023u)) & 1023u);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + AT_OFF_BAR);
-  uint64_t *q_full = bar, *k_full = bar + 1, *v_full = bar + 2, *k_free = bar + 3, *v_free = bar + 4, *s_ready = bar + 5,
-           *p_ready = bar + 6, *pv_done = bar + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + B_COUNT);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (k_len + AT_BK - 1) / AT_BK;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
-    mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(v_full, 1); mbar_init(k_free, 1); mbar_init(v_free, 1);
-    mbar_init(s_ready, 1); mbar_init(p_ready, 4); mbar_init(pv_done, 1);
+    for (int i = 0; i < B_COUNT; ++i) mbar_init(bar + i, (i == B_PREADY || i == B_PREADY + 1) ? 4 : 1);
     fence_barrier_init();
   }
-  if (warp == 1) tc5_alloc(tmem_slot, 256);
+  if (warp == 1) tc5_alloc(tmem_slot, AT_TMEM_COLS);
   tc5_fence_before();
   __syncthreads();
   tc5_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+  const uint32_t tmem_o = tmem_base + AT_TMEM_O;
 
   if (warp == 0) {
     if (lane == 0) {
       const int qrow = p.q_start[seq] + q0, krow = p.k_start[seq];
-      mbar_arrive_expect_tx(q_full, AT_Q_BYTES);
-      tma_load_2d(smem + AT_OFF_Q, &tmap_q, q_full, head * AT_HD, qrow);
-      for (int j = 0; j < n_tiles; ++j) {
-        const uint32_t ph = j & 1;
-        mbar_wait(k_free, ph ^ 1);
-        mbar_arrive_expect_tx(k_full, AT_K_BYTES);
-        tma_load_2d(smem + AT_OFF_K, &tmap_k, k_full, head * AT_HD, krow + j * AT_BK);
-        mbar_wait(v_free, ph ^ 1);
-        mbar_arrive_expect_tx(v_full, AT_V_BYTES);
-        tma_load_2d(smem + AT_OFF_V, &tmap_v, v_full, head * AT_HD, krow + j * AT_BK);
+      mbar_arrive_expect_tx(bar + B_QFULL, AT_Q_BYTES);
+      tma_load_2d(smem + AT_OFF_Q, &tmap_q, bar + B_QFULL, head * AT_HD, qrow);
+      // K runs AT_KLEAD tiles ahead of V: S_{j+2} is issued two tiles before PV_j, and a V slot only frees when its PV
+      // has committed -- a strictly alternating K_j, V_j order would hold K_{j+2} back behind V_{j+1}.
+      Ring kr, vr;
+      for (int i = 0; i < n_tiles + AT_KLEAD; ++i) {
+        if (i < n_tiles) {
+          mbar_wait(bar + B_KFREE + kr.slot, kr.phase ^ 1);
+          mbar_arrive_expect_tx(bar + B_KFULL + kr.slot, AT_KV_BYTES);
+          tma_load_2d(smem + AT_OFF_K + kr.slot * AT_KV_BYTES, &tmap_k, bar + B_KFULL + kr.slot, head * AT_HD, krow + i * AT_BK);
+          kr.next(AT_KST);
+        }
+        if (i >= AT_KLEAD) {
+          mbar_wait(bar + B_VFREE + vr.slot, vr.phase ^ 1);
+          mbar_arrive_expect_tx(bar + B_VFULL + vr.slot, AT_KV_BYTES);
+          tma_load_2d(smem + AT_OFF_V + vr.slot * AT_KV_BYTES, &tmap_v, bar + B_VFULL + vr.slot, head * AT_HD,
+                      krow + (i - AT_KLEAD) * AT_BK);
+          vr.next(AT_VST);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = at_idesc(AT_BQ, AT_BK, 0);   // S = Q K^T : B (= K tile) K-major
-      constexpr uint32_t idesc_o = at_idesc(AT_BQ, AT_HD, 1);   // O = P V   : B (= V tile) MN-major
+      constexpr uint32_t idesc_o = at_idesc(AT_BQ, AT_HD, 1);   // O += P V  : B (= V tile) MN-major
       const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + AT_OFF_Q));
-      const uint64_t dk = umma_desc_k_sw128(smem_u32(smem + AT_OFF_K));
-      const uint64_t dp = umma_desc_k_sw128(smem_u32(smem + AT_OFF_P));
-      const uint64_t dv = umma_desc_mn_sw128(smem_u32(smem + AT_OFF_V));
-      mbar_wait(q_full, 0);
+      Ring kr, sr;   // position of the next S tile to issue
+      auto issue_s = [&]() {
+        mbar_wait(bar + B_KFULL + kr.slot, kr.phase);
+        tc5_fence_after();
+        const uint64_t dk = umma_desc_k_sw128(smem_u32(smem + AT_OFF_K + kr.slot * AT_KV_BYTES));
+#pragma unroll
+        for (int k = 0; k < AT_HD / 16; ++k) tc5_mma_f16(tmem_base + sr.slot * AT_BK, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        tc5_commit(bar + B_KFREE + kr.slot);
+        tc5_commit(bar + B_SREADY + sr.slot);
+        kr.next(AT_KST);
+        sr.next(AT_SST);
+      };
+      mbar_wait(bar + B_QFULL, 0);
+      if (n_tiles > 0) issue_s();
+      if (n_tiles > 1) issue_s();
+      Ring vr, pr;
       for (int j = 0; j < n_tiles; ++j) {
-        const uint32_t ph = j & 1;
-        // S_j (the previous S was fully consumed before p_ready[j-1] was signalled)
-        mbar_wait(k_full, ph);
+        if (j + 2 < n_tiles) issue_s();   // its slot was last read by tile j-1: released by p_ready(j-1), waited below
+        mbar_wait(bar + B_PREADY + pr.slot, pr.phase);
+        mbar_wait(bar + B_VFULL + vr.slot, vr.phase);
         tc5_fence_after();
+        const uint64_t dp = umma_desc_k_sw128(smem_u32(smem + AT_OFF_P + pr.slot * AT_P_BYTES));
+        const uint64_t dv = umma_desc_mn_sw128(smem_u32(smem + AT_OFF_V + vr.slot * AT_KV_BYTES));
 #pragma unroll
-        for (int k = 0; k < AT_HD / 16; ++k) tc5_mma_f16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        tc5_commit(k_free);
-        tc5_commit(s_ready);
-        // O_j = P_j V_j
-        mbar_wait(v_full, ph);
-        mbar_wait(p_ready, ph);
-        tc5_fence_after();
-#pragma unroll
-        for (int k = 0; k < AT_BK / 16; ++k) {
-          // A: 16 keys = 32 bytes inside the 128-byte row of P block (k / 4); B: 16 key rows = 2048 bytes of the V tile
-          const uint64_t da = dp + (uint64_t)((k >> 2) * (AT_BQ * 128 >> 4)) + 2 * (k & 3);
-          const uint64_t db = dv + (uint64_t)(k * (16 * 128 >> 4));
-          tc5_mma_f16(tmem_o, da, db, idesc_o, k != 0);
-        }
-        tc5_commit(v_free);
-        tc5_commit(pv_done);
+        for (int k = 0; k < AT_BK / 16; ++k)   // A: 16 keys = 32 B inside the 128-byte P row; B: 16 key rows = 2048 B of V
+          tc5_mma_f16(tmem_o, dp + 2 * k, dv + (uint64_t)(k * (16 * 128 >> 4)), idesc_o, (j != 0) || (k != 0));
+        tc5_commit(bar + B_VFREE + vr.slot);
+        tc5_commit(bar + B_PVDONE + pr.slot);
+        vr.next(AT_VST);
+        pr.next(2);
       }
     }
   } else {
@@ -139,118 +226,108 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int quad = warp & 3;
     const int row = quad * 32 + lane;                     // row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    float o_acc[AT_HD];
-#pragma unroll
-    for (int i = 0; i < AT_HD; ++i) o_acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
-    uint8_t* sp = smem + AT_OFF_P;
+    const uint32_t to = tmem_o + lane_off;
+    const float scale = p.scale_log2;
+    float m_used = -INFINITY, l_run = 0.f;
+    uint32_t ra[32], rb[32];
+    Ring sr, pr;   // score slot / P buffer of tile j
     for (int j = 0; j < n_tiles; ++j) {
-      const uint32_t ph = j & 1;
       const int kvalid = min(AT_BK, k_len - j * AT_BK);
-      mbar_wait(s_ready, ph);
+      const bool full_tile = kvalid == AT_BK;             // warp-uniform: only the last tile needs key masking
+      const uint32_t ts = tmem_base + sr.slot * AT_BK + lane_off;
+      uint8_t* sp = smem + AT_OFF_P + pr.slot * AT_P_BYTES;
+      mbar_wait(bar + B_SREADY + sr.slot, sr.phase);
+      if (j >= 2) mbar_wait(bar + B_PVDONE + pr.slot, pr.phase ^ 1);   // PV_{j-2} no longer reads this P buffer
       tc5_fence_after();
-      const bool full_tile = kvalid == AT_BK;  // warp-uniform: only the last tile of a sequence needs key masking
-      // pass 1: row max (the TMEM load of chunk c+1 is in flight while chunk c is reduced)
-      float mx = -INFINITY;
-      {
-        uint32_t ra[32], rb[32];
-        tc5_ld_32x32(tmem_s + lane_off, ra);
+      bool exact = (j == 0);
+      float rs[4];
+      for (;;) {
+        tc5_ld_32x32(ts, ra);
+        tc5_ld_32x32(ts + 32, rb);
+        tc5_wait_ld();
+        if (exact) {
+          // exact path: row maximum first, then move the reference point (and O, l with it)
+          float mx = full_tile ? chunk_max<true>(ra, 0, kvalid, -INFINITY) : chunk_max<false>(ra, 0, kvalid, -INFINITY);
+          mx = full_tile ? chunk_max<true>(rb, 1, kvalid, mx) : chunk_max<false>(rb, 1, kvalid, mx);
+          float m_new = fmaxf(m_used, mx * scale);
+          if (m_new == -INFINITY) m_new = 0.f;
+          if (j > 0) {
+            const float corr = ex2_approx(m_used - m_new);
+            // PV_{j-1} (other P buffer) has committed: tile j-1 is phase (j-1)>>1 of that barrier
+            mbar_wait(bar + B_PVDONE + (pr.slot ^ 1), pr.slot ? pr.phase : (pr.phase ^ 1));
+            tc5_fence_after();
+            tc5_ld_32x32(to, ra);
+            tc5_ld_32x32(to + 32, rb);
+            tc5_wait_ld();
 #pragma unroll
-        for (int c = 0; c < AT_BK / 32; c += 2) {
-          tc5_wait_ld();
-          tc5_ld_32x32(tmem_s + lane_off + (c + 1) * 32, rb);
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (full_tile || c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(ra[i]));
-          tc5_wait_ld();
-          if (c + 2 < AT_BK / 32) tc5_ld_32x32(tmem_s + lane_off + (c + 2) * 32, ra);
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (full_tile || (c + 1) * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(rb[i]));
-        }
-      }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-      // O_{j-1} is complete: fold it into the register accumulator, then rescale to the new maximum
-      if (j > 0) {
-        mbar_wait(pv_done, ph ^ 1);
-        tc5_fence_after();
-#pragma unroll
-        for (int c = 0; c < AT_HD / 32; ++c) {
-          uint32_t r[32];
-          tc5_ld_32x32(tmem_o + lane_off + c * 32, r);
-          tc5_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(r[i]);
-        }
-      }
-      const float corr = ex2_approx(m_run - m_safe);  // m_run = -inf -> 0
-      if (corr != 1.0f) {
-#pragma unroll
-        for (int i = 0; i < AT_HD; ++i) o_acc[i] *= corr;
-      }
-      l_run *= corr;
-      m_run = m_new;
-      // pass 2: P = exp2(S * scale - m), row sum, fp16 into the swizzled K-major layout
-      float rs = 0.f;
-      {
-        uint32_t r[32];
-        tc5_ld_32x32(tmem_s + lane_off, r);
-#pragma unroll
-        for (int c = 0; c < AT_BK / 32; ++c) {
-          tc5_wait_ld();
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_safe));
-            float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -m_safe));
-            if (!full_tile) {
-              if (c * 32 + i >= kvalid) p0 = 0.f;
-              if (c * 32 + i + 1 >= kvalid) p1 = 0.f;
+            for (int i = 0; i < 32; ++i) {
+              ra[i] = __float_as_uint(__uint_as_float(ra[i]) * corr);
+              rb[i] = __float_as_uint(__uint_as_float(rb[i]) * corr);
             }
-            rs += p0 + p1;
-            pk[i >> 1] = pack_half2(p0, p1);
+            tc5_st_32x32(to, ra);
+            tc5_st_32x32(to + 32, rb);
+            tc5_wait_st();
+            l_run *= corr;
+            tc5_ld_32x32(ts, ra);       // the score registers were used as scratch: read S_j again
+            tc5_ld_32x32(ts + 32, rb);
+            tc5_wait_ld();
           }
-          if (c + 1 < AT_BK / 32) tc5_ld_32x32(tmem_s + lane_off + (c + 1) * 32, r);  // in flight during the smem stores
-          // 32 columns = 4 chunks of 16 bytes; chunk index inside the 64-column block: (c & 1) * 4 + q
-          uint8_t* blk = sp + (c >> 1) * (AT_BQ * 128) + row * 128;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int chunk = ((c & 1) * 4 + q) ^ (row & 7);
-            *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          }
+          m_used = m_new;
         }
+        rs[0] = rs[1] = rs[2] = rs[3] = 0.f;
+        float tm[2] = {-INFINITY, -INFINITY};
+        if (full_tile) {
+          softmax_chunk<true>(ra, 0, kvalid, scale, m_used, rs, tm, sp, row);
+          softmax_chunk<true>(rb, 1, kvalid, scale, m_used, rs, tm, sp, row);
+        } else {
+          softmax_chunk<false>(ra, 0, kvalid, scale, m_used, rs, tm, sp, row);
+          softmax_chunk<false>(rb, 1, kvalid, scale, m_used, rs, tm, sp, row);
+        }
+        if (exact) break;
+        // stale reference point: acceptable while no row of this warp outgrew it by more than 2^8
+        const bool grew = fmaf(fmaxf(tm[0], tm[1]), scale, -m_used) > 8.f;
+        if (!__any_sync(0xffffffffu, grew)) break;
+        exact = true;   // redo this tile on the exact path (S is still in TMEM, P has not been published)
       }
-      l_run += rs;
+      l_run += (rs[0] + rs[1]) + (rs[2] + rs[3]);
       fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc5_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
+      if (lane == 0) mbar_arrive(bar + B_PREADY + pr.slot);
+      sr.next(AT_SST);
+      pr.next(2);
     }
-    // last O tile
     if (n_tiles > 0) {
-      mbar_wait(pv_done, (n_tiles - 1) & 1);
+      const int last = n_tiles - 1;   // tile `last` is phase last>>1 of PV barrier last&1; PVs commit in order
+      mbar_wait(bar + B_PVDONE + (last & 1), (last >> 1) & 1);
       tc5_fence_after();
+      tc5_ld_32x32(to, ra);
+      tc5_ld_32x32(to + 32, rb);
+      tc5_wait_ld();
+    } else {
 #pragma unroll
-      for (int c = 0; c < AT_HD / 32; ++c) {
-        uint32_t r[32];
-        tc5_ld_32x32(tmem_o + lane_off + c * 32, r);
-        tc5_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(r[i]);
-      }
+      for (int i = 0; i < 32; ++i) ra[i] = rb[i] = 0u;
     }
     if (q0 + row < q_len) {
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       __half* og = p.O + (size_t)(p.q_start[seq] + q0 + row) * p.ldo + head * AT_HD;
 #pragma unroll
-      for (int i = 0; i < AT_HD; i += 8) {
+      for (int i = 0; i < 32; i += 8) {
         uint4 w;
-        w.x = pack_half2(o_acc[i] * inv, o_acc[i + 1] * inv);
-        w.y = pack_half2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
-        w.z = pack_half2(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
-        w.w = pack_half2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
+        w.x = pack_half2(__uint_as_float(ra[i]) * inv, __uint_as_float(ra[i + 1]) * inv);
+        w.y = pack_half2(__uint_as_float(ra[i + 2]) * inv, __uint_as_float(ra[i + 3]) * inv);
+        w.z = pack_half2(__uint_as_float(ra[i + 4]) * inv, __uint_as_float(ra[i + 5]) * inv);
+        w.w = pack_half2(__uint_as_float(ra[i + 6]) * inv, __uint_as_float(ra[i + 7]) * inv);
         *reinterpret_cast<uint4*>(og + i) = w;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 w;
+        w.x = pack_half2(__uint_as_float(rb[i]) * inv, __uint_as_float(rb[i + 1]) * inv);
+        w.y = pack_half2(__uint_as_float(rb[i + 2]) * inv, __uint_as_float(rb[i + 3]) * inv);
+        w.z = pack_half2(__uint_as_float(rb[i + 4]) * inv, __uint_as_float(rb[i + 5]) * inv);
+        w.w = pack_half2(__uint_as_float(rb[i + 6]) * inv, __uint_as_float(rb[i + 7]) * inv);
+        *reinterpret_cast<uint4*>(og + 32 + i) = w;
       }
     }
   }
@@ -258,7 +335,7 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   __syncthreads();
   if (warp == 1) {
     tc5_fence_after();
-    tc5_dealloc(tmem_base, 256);
+    tc5_dealloc(tmem_base, AT_TMEM_COLS);
   }
 }
 

@@ -196,7 +196,13 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           *reinterpret_cast<float4*>(stg + lane * 36 + j) =
               make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
         __syncwarp();
-        if (c + 1 < n_chunks) tc5_ld_32x32(taddr0 + (c + 1) * 32, r);  // in flight while this chunk is stored
+        if (c + 1 < n_chunks) {
+          tc5_ld_32x32(taddr0 + (c + 1) * 32, r);  // in flight while this chunk is stored
+        } else {
+          // accumulator fully read out (tcgen05.wait::ld above): release it before the last chunk's stores
+          tc5_fence_before();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
         const float4 bb = *reinterpret_cast<const float4*>(sbias + c * 32 + c4);
         float s4[4] = {1.f, 1.f, 1.f, 1.f};
         if constexpr (KIND == E_F32_ACC || KIND == E_GENERIC) {
@@ -229,9 +235,6 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
         __syncwarp();  // every lane is done with the staging tile before the next chunk overwrites it
       }
-      tc5_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
   }
 

@@ -70,7 +70,7 @@ M5_DEVINL void mbar_arrive_leader(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n"
       ::"r"(smem_u32(bar))
       : "memory");
 }
@@ -224,7 +224,14 @@ gemm_tc5_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           *reinterpret_cast<float4*>(stg + lane * 36 + j) =
               make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
         __syncwarp();
-        if (c + 1 < n_chunks) tc5_ld_32x32(taddr0 + (c + 1) * 32, r);
+        if (c + 1 < n_chunks) {
+          tc5_ld_32x32(taddr0 + (c + 1) * 32, r);
+        } else {
+          // the accumulator has been read out completely (tcgen05.wait::ld above): hand it back to the MMA warp now,
+          // the stores of this last chunk overlap the next tile's MMAs
+          tc5_fence_before();
+          if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+        }
         const float4 bb = *reinterpret_cast<const float4*>(sbias + c * 32 + c4);
         float s4[4] = {1.f, 1.f, 1.f, 1.f};
         if constexpr (KIND == E_F32_ACC || KIND == E_GENERIC) {
@@ -255,9 +262,6 @@ gemm_tc5_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         }
         __syncwarp();
       }
-      tc5_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
     }
   }
 
