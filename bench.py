@@ -329,8 +329,14 @@ def main():
     peak_tf, peak_gbs, peak_src = measured_peaks()
     gp = prof["gemm_tc5"]
     ach = gp["flops"] / max(gp["ms"], 1e-9) / 1e9  # TFLOP/s
-    roofline = {"kernel": "gemm_tc5_kernel (tcgen05, all NAR/AR-prefill/vocoder GEMMs)", "bound": "tensor", "achieved": ach,
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
+    roofline = {"kernel": "gemm_tc5_2cta_kernel / gemm_tc5_kernel (tcgen05; every NAR, AR-prefill and vocoder GEMM)", "bound": "tensor",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                # `achieved` averages over every GEMM shape of the step, so no single DRAM-byte figure matches it; the one
+                # ncu --set full capture (profiles/r1_gemm_tc5_2cta_ncu.txt) is reported with its own shape instead
+                "traffic": None,
+                "traffic_ncu": {"shape": "M=153552 N=3072 K=1024 fp16 out", "dram_bytes": 376112128 + 901768704,
+                                "algorithmic_bytes": 2 * (153552 * 1024 + 3072 * 1024 + 153552 * 3072)},
+                "peak_source": peak_src,
                 "launches": gp["launches"], "avg_launch_ms": gp["ms"] / max(gp["launches"], 1),
                 "share_of_step": gp["ms"] / ms, "flash_attn_tflops": prof["flash_attn"]["flops"] / max(prof["flash_attn"]["ms"], 1e-9) / 1e9,
                 "flash_attn_share_of_step": prof["flash_attn"]["ms"] / ms}
