@@ -147,6 +147,33 @@ int m5_ar_forward(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int32
 int m5_vocode(m5_ctx* ctx, int32_t B, const int32_t* codes, const int32_t* n_frames, int32_t bandwidth_id,
               int32_t mem, float* wav_out);
 
+/* ---- Tokenisers either side of the path (host code, no GPU work) ----------------------------
+ * Merge engine for the two "minbpe v1" tokenisers: text (base = 256 bytes, mars5/minbpe/regex.py) and speech
+ * (base = 1024 Encodec L0 codes, mars5/minbpe/codebook.py).  The regex split of text into chunks and the special-token
+ * handling stay with the caller (mars5_tts_b200/bpe.py mirrors RegexTokenizer / CodebookTokenizer on top of this). */
+typedef struct m5_bpe m5_bpe;
+
+/* merges[n_merges][2]: pair i creates token id base + i -- the line order of the model file
+ * (Tokenizer.load, minbpe/base.py:140-168; CodebookTokenizer.load, minbpe/codebook.py:178-205). */
+int m5_bpe_create(int32_t base, const int32_t* merges, int32_t n_merges, m5_bpe** out);
+void m5_bpe_destroy(m5_bpe* bpe);
+
+/* Applies the merge table to n_seq independent id sequences, sequence s = ids[offsets[s] .. offsets[s+1]), exactly like
+ * `_encode_chunk` (regex.py:92-111 / codebook.py:96-115): repeatedly the adjacent pair with the lowest merge index, all of
+ * its non-overlapping occurrences left to right.  Sequence s is written to out_ids + offsets[s] (out_ids may alias ids),
+ * its new length to out_len[s].  n_threads <= 0: one per hardware thread (capped by n_seq). */
+int m5_bpe_encode(const m5_bpe* bpe, const int32_t* ids, const int64_t* offsets, int32_t n_seq, int32_t* out_ids,
+                  int32_t* out_len, int32_t n_threads);
+
+/* Expands tokens into base symbols (what Tokenizer.decode / CodebookTokenizer.decode_int produce, regex.py:77-90,
+ * codebook.py:74-94).  An id outside the merge table must be one of special_ids and is emitted as -(k+1), k its index
+ * in special_ids; any other id is an error (the reference raises ValueError).  Returns the number of symbols (also
+ * when out_syms is NULL: size query), or -M5_ERR_ARG.  out_offsets[n_seq+1] (optional) receives the per-sequence
+ * boundaries. */
+int64_t m5_bpe_expand(const m5_bpe* bpe, const int32_t* ids, const int64_t* offsets, int32_t n_seq,
+                      const int32_t* special_ids, int32_t n_special, int32_t* out_syms, int64_t* out_offsets,
+                      int64_t capacity);
+
 /* ---- kernel-level entry points (device pointers) used by tests/ and bench.py's roofline leg -------------- */
 int m5_dbg_gemm(m5_ctx* ctx, const void* A_f16, const void* W_f16, int32_t M, int32_t N, int32_t K, int32_t kwrap,
                 const float* bias, const float* colscale, void* out, void* out_lo, int32_t ldc, int32_t mode,

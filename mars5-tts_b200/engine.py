@@ -230,21 +230,20 @@ class Mars5TTS:
     """Drop-in for the reference's Mars5TTS (inference.py:79-307) on the hot path.
 
     ``ar_ckpt`` / ``nar_ckpt``: the dicts hubconf.py builds ({'vocab': {...}, 'model': state_dict}).  The text /
-    speech tokenisers are built from ``ar_ckpt['vocab']`` with the reference's minbpe when it is importable, or passed
-    in (``texttok`` / ``speechtok``); ``codec`` must offer ``encode(wav[None]) -> [(codes (1, 8, T), scale)]`` like
+    speech tokenisers are built from the "minbpe v1" models in ``ar_ckpt['vocab']`` (mars5_tts_b200.bpe, native merge
+    engine) or passed in (``texttok`` / ``speechtok``: anything with the reference tokenisers' interface); ``codec`` must offer ``encode(wav[None]) -> [(codes (1, 8, T), scale)]`` like
     EncodecModel; ``vocos_state`` is the state dict of Vocos("charactr/vocos-encodec-24khz") (weight-norm removed).
     """
 
     def __init__(self, ar_ckpt, nar_ckpt, device: Optional[str] = None, *, vocos_state=None, texttok=None,
                  speechtok=None, codec=None):
         if texttok is None or speechtok is None:
-            import io
-            from mars5.minbpe.codebook import CodebookTokenizer  # reference package (pure-Python, out of scope)
-            from mars5.minbpe.regex import GPT4_SPLIT_PATTERN, RegexTokenizer
-            texttok = RegexTokenizer(GPT4_SPLIT_PATTERN)
-            texttok.load(io.BytesIO(ar_ckpt["vocab"]["texttok.model"].encode("utf-8")))
-            speechtok = CodebookTokenizer(GPT4_SPLIT_PATTERN)
-            speechtok.load(io.BytesIO(ar_ckpt["vocab"]["speechtok.model"].encode("utf-8")))
+            # "minbpe v1" model texts stored in the checkpoint (inference.py:92-99), on the native merge engine (bpe.py)
+            from . import bpe
+            texttok = bpe.RegexTokenizer(bpe.GPT4_SPLIT_PATTERN)
+            texttok.load(ar_ckpt["vocab"]["texttok.model"])
+            speechtok = bpe.CodebookTokenizer(bpe.GPT4_SPLIT_PATTERN)
+            speechtok.load(ar_ckpt["vocab"]["speechtok.model"])
         self.texttok, self.speechtok, self.codec = texttok, speechtok, codec
         dev_index = torch.device(device).index if device not in (None, "cuda") else None
         self.device = torch.device("cuda", dev_index or 0)
@@ -308,12 +307,15 @@ class Mars5TTS:
             ids, hit, _ = eng.ar_generate([p["prompt"] for p in chunk], [p["spk_ref"] for p in chunk],
                                           [p["n_phones"] for p in chunk], acfg, seed=seed,
                                           utt_ids=list(range(s, s + len(chunk))))
-            l0s = []
+            toks = []
             for p, seq, h in zip(chunk, ids, hit):
                 if h:
                     logging.warning(f"[autoregressive generation] output length = {len(seq)} -- inference likely failed or input too long!")
-                toks = np.clip(seq.astype(np.int64) - len(tt.vocab), 0, None)[p["first_codec_idx"]:].tolist()
-                l0s.append(np.asarray([c for c in self.speechtok.decode_int(toks) if type(c) == int], dtype=np.int32))
+                toks.append(np.clip(seq.astype(np.int64) - len(tt.vocab), 0, None)[p["first_codec_idx"]:].tolist())
+            # speech BPE -> Encodec L0 codes for the whole chunk at once when the tokeniser offers it (bpe.py)
+            dec = (self.speechtok.decode_int_batch(toks) if hasattr(self.speechtok, "decode_int_batch")
+                   else [self.speechtok.decode_int(t) for t in toks])
+            l0s = [np.asarray([c for c in d if type(c) == int], dtype=np.int32) for d in dec]
             ncfg = eng.make_nar_cfg(cfg, T=self.default_T)
             codes = eng.nar_infer([p["text_tokens"] for p in chunk], [p["spk_ref"] for p in chunk], l0s, ncfg, seed=seed,
                                   utt_ids=list(range(s, s + len(chunk))))

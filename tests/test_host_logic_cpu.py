@@ -44,3 +44,38 @@ def test_synthetic_tokenizers_and_bench_workload():
     wl = bench.make_workload(synth.FULL, 2, 0)
     assert wl["N"] == 1500 and len(wl["prompts"][0]) == 137 + 450 and wl["first_codec_idx"] == 138
     assert abs(wl["audio_s"] - 2 * 1499 / 75) < 1e-9 and wl["max_len"] == 587 + 1502
+
+
+def test_prepare_builds_the_reference_prompt_with_native_tokenisers():
+    """Host glue of Mars5TTS.tts (inference.py:212-258) with the bpe.py tokenisers: prompt = text tokens (+ offset speech
+    tokens of the reference clip when deep cloning), first_codec_idx, character-count EOS estimate."""
+    import io, json, os
+    import torch
+    from mars5_tts_b200 import bpe
+    from mars5_tts_b200.engine import InferenceConfig, Mars5TTS
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bpe_golden.json"), encoding="utf-8"))
+    tt = bpe.RegexTokenizer(); tt.load(gold["text"]["model"])
+    st = bpe.CodebookTokenizer(bpe.GPT4_SPLIT_PATTERN); st.load(io.BytesIO(gold["speech"]["model"].encode("utf-8")))
+    case = gold["speech"]["cases"][5]                      # 450 prompt frames with reference-made ids
+
+    class Codec:                                           # EncodecModel.encode stand-in: (1, 8, T) codes
+        def encode(self, wav):
+            codes = torch.zeros(1, 8, len(case["codes"]), dtype=torch.long)
+            codes[0, 0] = torch.tensor(case["codes"])
+            return [(codes, None)]
+
+    m = object.__new__(Mars5TTS)                           # no GPU context: only the host glue is exercised
+    m.texttok, m.speechtok, m.codec, m.sr = tt, st, Codec(), 24000
+    cfg = InferenceConfig(deep_clone=True)
+    p = m._prepare("Hello world, it's me!", torch.zeros(24000), "ka to mi", cfg)
+    text_ids = tt.encode("<|startoftext|>ka to mi Hello world, it's me!<|endoftext|>", allowed_special="all")
+    assert p["text_tokens"] == text_ids
+    assert p["prompt"] == text_ids + [i + len(tt.vocab) for i in case["ids"]]
+    assert p["first_codec_idx"] == len(text_ids) + 1
+    assert p["spk_ref"].shape == (450, 8) and p["n_phones"] == round(cfg.eos_estimated_gen_length_factor * len("Hello world, it's me!"))
+    shallow = m._prepare("Hello", torch.zeros(24000), None, InferenceConfig(deep_clone=False))
+    assert shallow["prompt"] == tt.encode("<|startoftext|>Hello<|endoftext|>", allowed_special="all")
+    assert shallow["first_codec_idx"] == len(shallow["prompt"]) + 1
+    import pytest
+    with pytest.raises(AssertionError):
+        m._prepare("x", torch.zeros(24000), None, cfg)     # deep clone without a transcript (inference.py:212-214)
