@@ -1,8 +1,7 @@
 """CPU micro-benchmark of the tokeniser stage between the AR and NAR loops at the BASELINE
 configs[2] batch: 32 utterances x (450-frame prompt L0 codes -> speech BPE, ~135-token text -> text BPE, ~1000 generated
-speech tokens -> decode_int).  Native merge engine (csrc/bpe.cu, batched, threaded) vs the pure-Python restatement of the
-reference loops (oracle/bpe_oracle.py) and -- when /root/reference is present (build container only) -- the unmodified
-reference classes.  Tokeniser models: the golden fixtures' (trained by the reference on synthetic corpora).
+speech tokens -> decode_int).  Native merge engine (csrc/bpe.cu, batched, threaded) vs -- when /root/reference is present
+(build container only) -- the unmodified reference classes, whose outputs are also compared.  Tokeniser models: the golden fixtures' (trained by the reference on synthetic corpora).
 
     python tools/bpe_bench.py > profiles/r1_bpe_cpu.txt
 """
@@ -15,15 +14,12 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from mars5_tts_b200 import bpe  # noqa: E402
-from oracle import bpe_oracle  # noqa: E402
 
 gold = json.load(open(os.path.join(ROOT, "tests", "golden", "bpe_golden.json"), encoding="utf-8"))
 rng = random.Random(7)
 B = 32
 sp = bpe.CodebookTokenizer(bpe.GPT4_SPLIT_PATTERN); sp.load(gold["speech"]["model"])
 tx = bpe.RegexTokenizer(); tx.load(gold["text"]["model"])
-_, sp_specials, sp_pairs = bpe.parse_model(gold["speech"]["model"])
-sp_table = bpe_oracle.merge_table(sp_pairs, 1024)
 # inputs with the statistics of the golden corpus (so that merges actually fire)
 hot = sorted({c for case in gold["speech"]["cases"] for c in case["codes"]})[:40]
 prompts = [[rng.choice(hot) if rng.random() < 0.85 else rng.randrange(1024) for _ in range(450)] for _ in range(B)]
@@ -40,13 +36,11 @@ def best(fn, reps=5):
 
 rows = []
 t_native_enc = best(lambda: sp.encode_codes_batch(prompts))
-t_oracle_enc = best(lambda: [bpe_oracle.encode_chunk(p, sp_table) for p in prompts], reps=2)
-rows.append(("speech BPE encode, 32 x 450 codes", t_native_enc, t_oracle_enc))
+rows.append(("speech BPE encode, 32 x 450 codes", t_native_enc))
 t_native_dec = best(lambda: sp.decode_int_batch(gen))
-t_oracle_dec = best(lambda: [bpe_oracle.decode_int(g, sp_pairs, 1024, sp_specials) for g in gen], reps=2)
-rows.append((f"decode_int, 32 x {len(gen[0])} tokens -> 1500 codes", t_native_dec, t_oracle_dec))
+rows.append((f"decode_int, 32 x {len(gen[0])} tokens -> 1500 codes", t_native_dec))
 t_native_txt = best(lambda: tx.encode_batch(texts))
-rows.append((f"text BPE encode, 32 texts (~{sum(map(len, texts)) // B} chars)", t_native_txt, None))
+rows.append((f"text BPE encode, 32 texts (~{sum(map(len, texts)) // B} chars)", t_native_txt))
 
 ref = {}
 if os.path.isdir("/root/reference/mars5"):
@@ -64,13 +58,11 @@ if os.path.isdir("/root/reference/mars5"):
     ref[rows[1][0]] = best(lambda: [rsp.decode_int(g) for g in gen], reps=2)
     ref[rows[2][0]] = best(lambda: [rtx.encode(t) for t in texts], reps=2)
 
-print(f"# tools/bpe_bench.py on {os.cpu_count()} host threads; best of 5 (native) / 2 (Python); batch = {B} utterances")
-print(f"# {'stage':58s} {'native':>10s} {'oracle port':>12s} {'reference':>11s}  speed-up vs reference (or port)")
-for name, tn, to in rows:
+print(f"# tools/bpe_bench.py on {os.cpu_count()} host threads; best of 5 (native) / 2 (reference); batch = {B} utterances")
+print(f"# {'stage':58s} {'native':>10s} {'reference':>11s}  speed-up")
+for name, tn in rows:
     tr = ref.get(name)
-    base = tr if tr is not None else to
-    print(f"  {name:58s} {tn * 1e3:8.2f} ms {('%9.1f ms' % (to * 1e3)) if to else '           -'} "
-          f"{('%8.1f ms' % (tr * 1e3)) if tr else '          -'}  {base / tn:7.1f}x" if base else f"  {name:58s} {tn * 1e3:8.2f} ms")
+    print(f"  {name:58s} {tn * 1e3:8.2f} ms " + (f"{tr * 1e3:8.1f} ms  {tr / tn:7.1f}x" if tr else "          -"))
 tot_n = sum(r[1] for r in rows)
 tot_r = sum(ref.values()) if ref else None
 print(f"# host time per batch of 32 between/around the GPU stages: native {tot_n * 1e3:.1f} ms"
