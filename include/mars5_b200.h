@@ -174,6 +174,14 @@ int64_t m5_bpe_expand(const m5_bpe* bpe, const int32_t* ids, const int64_t* offs
                       const int32_t* special_ids, int32_t n_special, int32_t* out_syms, int64_t* out_offsets,
                       int64_t capacity);
 
+/* ---- Silence trim after the vocoder (host code) -----------------------------------------------
+ * Replaces trim() of mars5/trim.py:110-177 as called at inference.py:305: for waveform b = wav[offsets[b] ..
+ * offsets[b+1]) (host, fp32 mono) the sample range [start[b], end[b]) from the first to one past the last frame whose
+ * mean power is within top_db of the loudest frame (frames of frame_length every hop_length samples of the reflect-padded
+ * signal); (0, 0) when no frame qualifies.  A waveform not longer than frame_length/2 is an error, as in the reference. */
+int m5_trim_bounds(int32_t B, const float* wav, const int64_t* offsets, float top_db, int32_t frame_length,
+                   int32_t hop_length, int64_t* start, int64_t* end, int32_t n_threads);
+
 /* ---- kernel-level entry points (device pointers) used by tests/ and bench.py's roofline leg -------------- */
 int m5_dbg_gemm(m5_ctx* ctx, const void* A_f16, const void* W_f16, int32_t M, int32_t N, int32_t K, int32_t kwrap,
                 const float* bias, const float* colscale, void* out, void* out_lo, int32_t ldc, int32_t mode,

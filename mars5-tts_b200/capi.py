@@ -66,6 +66,7 @@ _SIGS = {
     "m5_dbg_sample": (_I, [_P, _P, _I, _I, C.POINTER(ArCfg), _I, _P, _I, _P, _P, _P, C.c_uint64, _P, _P]),
     "m5_dbg_posterior": (_I, [_P, _P, _P, _I, _I, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, C.c_uint64, _P]),
     "m5_dbg_istft": (_I, [_P, _P, _I, _P, _P]),
+    "m5_trim_bounds": (_I, [_I, _P, _P, C.c_float, _I, _I, _P, _P, _I]),
     "m5_bpe_create": (_I, [_I, _P, _I, C.POINTER(_P)]),
     "m5_bpe_destroy": (None, [_P]),
     "m5_bpe_encode": (_I, [_P, _P, _P, _I, _P, _P, _I]),

@@ -16,7 +16,9 @@ from typing import List, Optional
 import numpy as np
 import torch
 
-from . import capi, weights
+from . import capi
+from . import weights
+from .trim import trim_bounds_batch
 
 
 @dataclass
@@ -324,14 +326,16 @@ class Mars5TTS:
                 skip = len(p["spk_ref"]) if cfg.deep_clone else 0  # second crop of inference.py:300-301
                 outs.append(c[skip:])
             wavs = eng.vocode(outs, bandwidth_id=1)
-            for i, (l0, w) in enumerate(zip(l0s, wavs)):
-                results[s + i] = (torch.from_numpy(l0.astype(np.int64)).to(self.device), torch.from_numpy(w))
+            # vocode final output and trim silences (inference.py:304-305), the whole chunk at once
+            bounds = trim_bounds_batch(wavs, top_db=cfg.trim_db)
+            for i, (l0, w, (a, b)) in enumerate(zip(l0s, wavs, bounds)):
+                results[s + i] = (torch.from_numpy(l0.astype(np.int64)).to(self.device), torch.from_numpy(w[a:b].copy()))
         return results
 
     @torch.inference_mode()
     def tts(self, text: str, ref_audio: torch.Tensor, ref_transcript: Optional[str] = None,
             cfg: Optional[InferenceConfig] = InferenceConfig()):
-        """Same contract as the reference's tts() (inference.py:201-307) minus the CPU silence trim (mars5/trim.py is
-        outside the hot path and broken under numpy 2; apply it to the returned audio if wanted)."""
+        """Same contract as the reference's tts() (inference.py:201-307): (AR L0 codes on the device, trimmed 24 kHz
+        waveform on the CPU)."""
         codes, wav = self.tts_batch([text], [ref_audio], [ref_transcript], cfg)[0]
         return codes, wav

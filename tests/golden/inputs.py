@@ -40,3 +40,27 @@ def make_inputs():
     d["post_u"] = torch.rand(2, Sx, 8, 1025, generator=g)
     d["size"], d["n_text"], d["V"], d["eos"] = size, n_text, V, n_text + 1024
     return d
+
+
+def trim_cases():
+    """Seeded mono waveforms for the silence-trim fixtures (make_trim_golden.py / tests/test_trim_cpu.py): speech-like
+    bursts between stretches of low-level noise, at 24 kHz.  Returns a list of (name, float32 tensor)."""
+    g = torch.Generator().manual_seed(4321)
+    cases = []
+
+    def burst(n, segs, floor):
+        env = torch.zeros(n)
+        for a, b, amp in segs:
+            env[a:b] = amp
+        return (torch.randn(n, generator=g) * env + floor * torch.randn(n, generator=g)).float()
+
+    cases.append(("lead_tail_silence", burst(48000, [(9000, 30000, 0.3)], 1e-4)))
+    cases.append(("two_bursts", burst(60001, [(5000, 12000, 0.2), (40000, 52000, 0.05)], 1e-4)))
+    cases.append(("no_silence", burst(24000, [(0, 24000, 0.1)], 0.0)))
+    cases.append(("quiet_tail_above_threshold", burst(36000, [(2000, 20000, 0.5), (20000, 36000, 0.03)], 1e-5)))
+    cases.append(("quiet_tail_below_threshold", burst(36000, [(2000, 20000, 0.5), (20000, 36000, 0.01)], 1e-5)))
+    cases.append(("all_zero", torch.zeros(8000)))
+    cases.append(("digital_silence_then_click", burst(20000, [(15000, 15040, 0.9)], 0.0)))
+    cases.append(("full_utterance_length", burst(1499 * 320, [(30000, 420000, 0.25)], 3e-4)))
+    cases.append(("shortest_legal", burst(1025, [(100, 900, 0.2)], 1e-4)))
+    return cases

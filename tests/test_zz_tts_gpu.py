@@ -1,0 +1,66 @@
+"""End-to-end drop-in surface on the GPU: Mars5TTS.tts / tts_batch (inference.py:201-307) = tokenisers (bpe.py) -> AR
+-> speech-BPE decode -> NAR -> vocoder -> silence trim, on the tiny synthetic models.  Checks the glue, not the numerics
+(those are pinned kernel by kernel in test_pipeline_gpu.py): a batch row equals the single call, the stages chained by
+hand through Engine give the same codes and the same waveform, and the returned audio is the oracle's trim of it."""
+import numpy as np
+import pytest
+import torch
+
+from mars5_tts_b200 import bpe, synth
+from mars5_tts_b200.engine import InferenceConfig, Mars5TTS
+from oracle import trim_oracle
+
+pytestmark = pytest.mark.gpu
+
+TEXT_MODEL = "minbpe v1\n" + bpe.GPT4_SPLIT_PATTERN + "\n2\n<|startoftext|> 256\n<|endoftext|> 257\n"
+SPEECH_MODEL = "minbpe v1\n\n1\n<|endofspeech|> 1024\n"
+PF = 12
+
+
+class _Codec:
+    """EncodecModel.encode stand-in (inference.py:233): deterministic (1, 8, PF) codes from the clip's first sample."""
+
+    def encode(self, wav):
+        g = torch.Generator().manual_seed(int(abs(float(wav.flatten()[0])) * 1000) + 7)
+        return [(torch.randint(0, 1024, (1, 8, PF), generator=g), None)]
+
+
+@pytest.fixture(scope="module")
+def tts():
+    size = synth.TINY
+    ar = {"model": synth.make_ar_state(size), "vocab": {"texttok.model": TEXT_MODEL, "speechtok.model": SPEECH_MODEL}}
+    nar = {"model": synth.make_nar_state(size)}
+    m = Mars5TTS(ar, nar, "cuda:0", vocos_state=synth.make_vocos_state(size), codec=_Codec())
+    assert len(m.texttok.vocab) == 258 and len(m.speechtok.vocab) == 1025
+    yield m
+    m.engine.close()
+
+
+def test_tts_batch_rows_equal_single_calls_and_hand_chained_stages(tts):
+    cfg = InferenceConfig(generate_max_len_override=56, deep_clone=True)
+    texts, refs, trs = ["hello there", "b200"], [torch.full((2400,), 0.25), torch.full((2400,), 0.5)], ["ab cd", "xy"]
+    out = tts.tts_batch(texts, refs, trs, cfg)
+    assert len(out) == 2
+    for codes, wav in out:
+        assert codes.dtype == torch.long and codes.is_cuda and codes.dim() == 1 and codes.numel() > 0
+        assert wav.dtype == torch.float32 and not wav.is_cuda and wav.dim() == 1 and torch.isfinite(wav).all()
+    # single call == row 0 of the batch (results are keyed by utterance id, not by batch position or size)
+    c0, w0 = tts.tts(texts[0], refs[0], trs[0], cfg)
+    assert torch.equal(c0, out[0][0]) and torch.equal(w0, out[0][1])
+    # the same stages chained by hand through Engine
+    eng = tts.engine
+    preps = [tts._prepare(t, a, r, cfg) for t, a, r in zip(texts, refs, trs)]
+    eos = len(tts.texttok.vocab) + tts.speechtok.special_tokens["<|endofspeech|>"]
+    ids, hit, _ = eng.ar_generate([p["prompt"] for p in preps], [p["spk_ref"] for p in preps], [p["n_phones"] for p in preps],
+                                  eng.make_ar_cfg(cfg, 56, eos), seed=0, utt_ids=[0, 1])
+    l0s = []
+    for p, seq in zip(preps, ids):
+        toks = np.clip(seq.astype(np.int64) - 258, 0, None)[p["first_codec_idx"]:].tolist()
+        l0s.append(np.asarray([c for c in tts.speechtok.decode_int(toks) if type(c) == int], dtype=np.int32))
+    codes = eng.nar_infer([p["text_tokens"] for p in preps], [p["spk_ref"] for p in preps], l0s, eng.make_nar_cfg(cfg, T=tts.default_T),
+                          seed=0, utt_ids=[0, 1])
+    wavs = eng.vocode([c[PF:] for c in codes], bandwidth_id=1)
+    for (got_codes, got_wav), l0, w in zip(out, l0s, wavs):
+        assert got_codes.cpu().tolist() == l0.tolist()
+        a, b = trim_oracle.trim_bounds(torch.from_numpy(w), cfg.trim_db)
+        assert got_wav.numel() == b - a and torch.equal(got_wav, torch.from_numpy(w)[a:b])
