@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <new>
 
 #include "rowops.h"
 
@@ -90,7 +91,8 @@ int m5_create(int device, const m5_model_cfg* cfg, const m5_tensor* tensors, int
             prop.minor);
     return M5_ERR_STATE;
   }
-  m5_ctx* ctx = new m5_ctx();
+  m5_ctx* ctx = new (std::nothrow) m5_ctx();
+  if (!ctx) return M5_ERR_NOMEM;
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
   ctx->cfg = *cfg;
@@ -103,11 +105,15 @@ int m5_create(int device, const m5_model_cfg* cfg, const m5_tensor* tensors, int
   // RoPE inverse frequencies: 1 / (10000 ** (arange(0,64,2).float() / 64)) in fp32 (nn_future.py:194-198)
   float inv[32];
   for (int i = 0; i < 32; ++i) inv[i] = 1.0f / powf(10000.0f, (float)(2 * i) / 64.0f);
-  cudaMalloc(&ctx->rope_inv_freq, sizeof(inv));
-  cudaMemcpy(ctx->rope_inv_freq, inv, sizeof(inv), cudaMemcpyHostToDevice);
-  cudaMalloc(&ctx->skinny_scratch, gemm_skinny_scratch_bytes(ctx->num_sms));
-  cudaMalloc(&ctx->skinny_counters, 1024 * sizeof(int));
-  cudaMemset(ctx->skinny_counters, 0, 1024 * sizeof(int));
+  if (cudaMalloc(&ctx->rope_inv_freq, sizeof(inv)) != cudaSuccess ||
+      cudaMemcpy(ctx->rope_inv_freq, inv, sizeof(inv), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMalloc(&ctx->skinny_scratch, gemm_skinny_scratch_bytes(ctx->num_sms)) != cudaSuccess ||
+      cudaMalloc(&ctx->skinny_counters, 1024 * sizeof(int)) != cudaSuccess ||
+      cudaMemset(ctx->skinny_counters, 0, 1024 * sizeof(int)) != cudaSuccess) {
+    cudaGetLastError();
+    m5_destroy(ctx);   // frees whatever was allocated
+    return M5_ERR_NOMEM;
+  }
   // The caller may override the three derived tables with torch-computed ones (bit-exact with the reference):
   //   "tab.rope_inv_freq" [32], "tab.pe_ar" [max_pos, ar_dim], "tab.pe_nar" [max_pos, nar_dim]
   *out = ctx;
@@ -124,6 +130,8 @@ void m5_destroy(m5_ctx* ctx) {
   if (ctx->twiddle) cudaFree(ctx->twiddle);
   if (ctx->skinny_scratch) cudaFree(ctx->skinny_scratch);
   if (ctx->skinny_counters) cudaFree(ctx->skinny_counters);
+  prof_resolve(ctx);   // returns pending profiling events to the pool
+  for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
