@@ -79,3 +79,39 @@ def test_prepare_builds_the_reference_prompt_with_native_tokenisers():
     import pytest
     with pytest.raises(AssertionError):
         m._prepare("x", torch.zeros(24000), None, cfg)     # deep clone without a transcript (inference.py:212-214)
+
+
+def test_repack_consumes_the_released_checkpoint_layout():
+    """Every key of the reference's real-size state dicts (tests/golden/state_manifest.json: CodecLM / ResidualTransformer
+    built with inference.py:105-110's arguments on the meta device) is read by weights.repack and nothing else is
+    expected; the derived dimensions are the released models' (SURVEY.md Appendix A)."""
+    import json, os
+
+    m = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "state_manifest.json")))
+    assert len(m["ar"]) == 273 and len(m["nar"]) == 487
+
+    class Spy(dict):
+        def __init__(self, *a):
+            super().__init__(*a)
+            self.used = set()
+
+        def __getitem__(self, k):
+            self.used.add(k)
+            return super().__getitem__(k)
+
+    def tensors(shapes):   # shapes only (meta device); the learned PE scalars are read with .item() and must be real
+        return Spy({k: torch.full(v, 0.5) if k.endswith("alpha") else torch.empty(v, device="meta") for k, v in shapes.items()})
+
+    ar, nar = tensors(m["ar"]), tensors(m["nar"])
+    d = weights.dims_from_state(ar, nar, None, m["n_text"])
+    assert (d["ar_dim"], d["ar_heads"], d["ar_layers"], d["ar_hidden"], d["ar_vocab"], d["ar_spk_layers"], d["ar_spk_ff"]) == \
+        (1536, 24, 26, 3584, 8000, 2, 4608)
+    assert (d["nar_dim"], d["nar_heads"], d["nar_enc_layers"], d["nar_dec_layers"], d["nar_spk_layers"], d["nar_ff"], d["n_classes"],
+            d["n_quant"], d["nar_text_vocab"]) == (1024, 16, 8, 16, 3, 3072, 1025, 8, 2049)
+    t, alphas = weights.repack(ar, nar, None, d, max_pos=64)
+    assert set(ar) == ar.used and set(nar) == nar.used            # nothing in a real checkpoint is ignored
+    assert t["ar.l25.wqkv"].shape == (4608, 1536) and t["ar.l25.w13"].shape == (7168, 1536) and t["ar.output"].shape == (8000, 1536)
+    assert t["nar.dec.l15.ca_kv_w"].shape == (2048, 1024) and alphas["nar_ref_alpha"] == 0.5
+    # the synthetic FULL-size checkpoints of bench.py have exactly this layout
+    full = synth.FULL
+    assert full["n_text"] + full["n_speech"] == d["ar_vocab"] and full["ar_layers"] == d["ar_layers"] and full["nar_dec_layers"] == d["nar_dec_layers"]
