@@ -6,11 +6,17 @@ One "step" = one pass of the hot path over one batch of B synthetic utterances (
 to N = 15 frames per text token = 1500 frames (random weights never emit EOS), T = 200 reverse steps with classifier-free
 guidance.  value  = audio seconds / second with inputs resident in HBM; e2e = the same through the host-buffer C ABI.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size full|mid|tiny] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c5] [--mode fast|mixed|precise]
 
 N > 1: launched under torch.distributed.run, one rank per GPU; utterances shard by batch (weak scaling), weights are
-repacked on rank 0 and broadcast over NCCL, finished waveforms are all-gathered.  --impl reference times the CPU port of
-the reference (oracle/) on the host cores on a bounded sample of the same workload (rank 0 only).
+repacked on rank 0 and broadcast over NCCL, finished waveforms are all-gathered.  --impl reference times the reference's
+CPU path on the host cores on a bounded sample of the same workload (rank 0 only): the UNMODIFIED reference modules when
+/root/reference is importable (build container), otherwise the oracle port (GPU box).
+
+Wall budget: the driver kills a run after 870 s.  Warm-up passes are the full workload at T = 8 reverse steps (they
+touch every kernel and shape and size the workspace) except the last, which is a complete step and calibrates the step
+time; if K steps do not fit into M5_BENCH_BUDGET_S (default 780 s from process start) fewer steps are timed and the line
+says so (`steps` = measured, `steps_requested` = K).
 """
 import argparse
 import json
@@ -20,6 +26,8 @@ import sys
 import threading
 import time
 
+T_PROC0 = time.perf_counter()
+
 import numpy as np
 import torch
 
@@ -28,37 +36,47 @@ sys.path.insert(0, ROOT)
 
 METRIC = "audio sec/s synthesized (deep-clone, batch 32)"
 UNIT = "audio_s/s"
+BUDGET_S = float(os.environ.get("M5_BENCH_BUDGET_S", "780"))
+MODES = {"fast": 0, "precise": 1, "mixed": 2}
+
+
+def elapsed():
+    return time.perf_counter() - T_PROC0
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def make_workload(size, B, seed, n_text_tok=100, n_ref_tok=35, Pf=450, frames_per_tok=15, utt_base=0):
-    """Synthetic inputs of SURVEY.md 8(d): token ids stand in for tokenised text, codes for the Encodec-encoded clip."""
+def make_workload(size, B, seed, n_text_tok=100, n_ref_tok=35, Pf=450, frames_per_tok=15, utt_base=0, mixed=False):
+    """Synthetic inputs of SURVEY.md 8(d): token ids stand in for tokenised text, codes for the Encodec-encoded clip.
+    mixed: per-utterance text length ~ U{20..120} tokens (BASELINE configs[3])."""
     g = torch.Generator().manual_seed(seed)
     n_text = size["n_text"]
-    wl = dict(B=B, Pf=Pf, N=frames_per_tok * n_text_tok, n_text=n_text, prompts=[], spk=[], text=[], n_phones=[], utt=[])
+    wl = dict(B=B, Pf=Pf, n_text=n_text, prompts=[], spk=[], text=[], n_phones=[], utt=[], N_b=[])
     for b in range(B):
+        ntok = int(torch.randint(20, 121, (1,), generator=g)) if mixed else n_text_tok
         sot, eot = n_text - 2, n_text - 1
-        text_full = [sot] + torch.randint(0, n_text - 2, (n_ref_tok + n_text_tok,), generator=g).tolist() + [eot]
+        text_full = [sot] + torch.randint(0, n_text - 2, (n_ref_tok + ntok,), generator=g).tolist() + [eot]
         spk = torch.randint(0, 1024, (Pf, 8), generator=g).numpy().astype(np.int32)
         speech_prompt = (spk[:, 0] + n_text).tolist()  # ratio-1 synthetic speech tokenizer: one token per frame
         wl["prompts"].append(np.asarray(text_full + speech_prompt, dtype=np.int32))
         wl["spk"].append(spk)
         wl["text"].append(np.asarray(text_full, dtype=np.int32))
-        wl["n_phones"].append(5 * n_text_tok)
+        wl["n_phones"].append(5 * ntok)
         wl["utt"].append(utt_base + b)
+        wl["N_b"].append(frames_per_tok * ntok)
+    wl["N"] = max(wl["N_b"])
     wl["first_codec_idx"] = len(wl["text"][0]) + 1          # inference.py:256
-    wl["max_len"] = len(wl["prompts"][0]) + wl["N"] + 2      # generate_max_len_override so the sequence fits
-    wl["audio_s"] = B * (wl["N"] - 1) / 75.0                 # frames vocoded per utterance after both crops
+    wl["max_len"] = max(len(p) for p in wl["prompts"]) + wl["N"] + 2   # generate_max_len_override so the sequence fits
+    wl["audio_s"] = sum(n - 1 for n in wl["N_b"]) / 75.0     # frames vocoded per utterance after both crops
     return wl
 
 
-def run_step(eng, icfg, wl, T, precise, seed=0):
+def run_step(eng, icfg, wl, T, mode, seed=0):
     """AR -> (host glue of inference.py:272-283) -> NAR -> crop -> vocoder through the host-buffer API."""
     eos = eng.dims["ar_vocab"] - 1
     acfg = eng.make_ar_cfg(icfg, wl["max_len"], eos, force_len=wl["N"], sync_every=64)
     ids, _, _ = eng.ar_generate(wl["prompts"], wl["spk"], wl["n_phones"], acfg, seed=seed, utt_ids=wl["utt"])
     l0 = [((np.clip(s.astype(np.int64) - wl["n_text"], 0, None))[wl["first_codec_idx"]:] % 1024).astype(np.int32) for s in ids]
-    ncfg = eng.make_nar_cfg(icfg, T=T, precise=precise)
+    ncfg = eng.make_nar_cfg(icfg, T=T, precise=mode)
     codes = eng.nar_infer(wl["text"], wl["spk"], l0, ncfg, seed=seed, utt_ids=wl["utt"])
     outs = [c[wl["Pf"]:] for c in codes]                     # second crop, inference.py:300-301
     return eng.vocode(outs, bandwidth_id=1)
@@ -74,7 +92,7 @@ def to_device(wl, dev):
 PHASE_S = {"ar": 0.0, "nar": 0.0, "voc": 0.0}
 
 
-def run_step_device(eng, icfg, wl, dw, T, precise, seed=0):
+def run_step_device(eng, icfg, wl, dw, T, mode, seed=0):
     """Same step with every data buffer resident on the device (mem = M5_MEM_DEVICE); the glue is slicing on device."""
     B, N, Pf, fci = wl["B"], wl["N"], wl["Pf"], wl["first_codec_idx"]
     t0 = time.perf_counter()
@@ -86,7 +104,7 @@ def run_step_device(eng, icfg, wl, dw, T, precise, seed=0):
     t1 = time.perf_counter()
     l0 = ((out_ids[:, fci:L] - wl["n_text"]).clamp_(min=0) % 1024).to(torch.int32).reshape(-1).contiguous()
     xlen = [L - fci] * B
-    ncfg = eng.make_nar_cfg(icfg, T=T, precise=precise)
+    ncfg = eng.make_nar_cfg(icfg, T=T, precise=mode)
     codes = eng.nar_infer_packed(dw["text"], dw["tlen"], dw["codes"], dw["slen"], l0, xlen, ncfg, seed=seed, utt=wl["utt"])
     t2 = time.perf_counter()
     outs = codes.view(B, L - fci, 8)[:, Pf:].contiguous().view(-1, 8)
@@ -94,6 +112,16 @@ def run_step_device(eng, icfg, wl, dw, T, precise, seed=0):
     t3 = time.perf_counter()  # every C-ABI call returns after its stream has drained: host timers bracket device work
     PHASE_S["ar"] += t1 - t0; PHASE_S["nar"] += t2 - t1; PHASE_S["voc"] += t3 - t2
     return wav
+
+
+def run_step_nar_only(eng, icfg, wl, dw, T, mode, seed=0):
+    """BASELINE configs[4]: the multinomial-DDPM loop alone (L0 codes given), then the vocoder."""
+    B, Pf = wl["B"], wl["Pf"]
+    ncfg = eng.make_nar_cfg(icfg, T=T, precise=mode)
+    xl = Pf - 1 + wl["N"]                                    # what the AR stage would hand over (prompt frames re-decoded)
+    codes = eng.nar_infer_packed(dw["text"], dw["tlen"], dw["codes"], dw["slen"], dw["l0"], [xl] * B, ncfg, seed=seed, utt=wl["utt"])
+    outs = codes.view(B, xl, 8)[:, Pf:].contiguous().view(-1, 8)
+    return eng.vocode_packed(outs, [xl - Pf] * B, bandwidth_id=1)
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -130,13 +158,13 @@ def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops_sustained", 1370.8), d.get("hbm_gbs", 6569.6), "measured (MEASURED_PEAKS.json, sustained bf16)"
+        return d.get("bf16_tflops_sustained", 1370.8), d.get("hbm_gbs", 6569.6), "measured (MEASURED_PEAKS.json: sustained bf16, HBM copy)"
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
 def _thread_candidates():
     n = os.cpu_count() or 1
-    return sorted({c for c in (4, 8, 16, 32, 64, n) if c <= n})
+    return sorted({c for c in (8, 16, 32, 64, n) if c <= n})
 
 
 def _best_threads(run, candidates):
@@ -145,6 +173,7 @@ def _best_threads(run, candidates):
     best_t, best_n = float("inf"), candidates[0]
     for n in candidates:
         torch.set_num_threads(n)
+        run()                              # first call at a new pool size pays the thread start-up
         t0 = time.perf_counter()
         run()
         t = time.perf_counter() - t0
@@ -155,46 +184,142 @@ def _best_threads(run, candidates):
     return best_n, best_t
 
 
-def cpu_port_sample(size, wl, T, n_ar_steps=2):
-    """Times the CPU port of the reference (oracle/, fp32) on ONE utterance of the workload: prefill, a few KV-cached AR
-    decode steps right after the prompt and ONE NAR forward at full length (a reverse step = cond + uncond forward).
-    The intra-op thread count is chosen per phase by measurement (best of 4..all host threads).
-    Extrapolates audio_s/s = audio / (prefill + N * t_ar + T * t_nar).  Returns (value, detail dict)."""
+# ------------------------------------------------------------------------------------------------ CPU legs
+def cpu_port_sample(size, wl, T, budget_s=25.0):
+    """Times the CPU port of the reference (oracle/, fp32) on ONE utterance of the workload, bounded to ~budget_s:
+    KV-cached AR decode steps at the MEAN context of the utterance (cache pre-filled with random K/V; each step includes
+    the per-step speaker-encoder pass of the reference, model.py:109-127), ONE NAR model evaluation at full length
+    (a reverse step = cond + uncond evaluation) and ONE posterior step (CFG + q_posterior + both Gumbel draws).  The
+    prefill is charged at the measured per-token GEMM rate of the NAR evaluation.  Extrapolates
+    audio_s/s = audio / (N * t_ar + T * (2 * t_fwd + t_post)).  Returns (value, detail dict)."""
     from mars5_tts_b200 import synth, weights
     from oracle import ar_oracle, nar_oracle
+    t_begin = time.perf_counter()
     cands = _thread_candidates()
     ar_sd, nar_sd = synth.make_ar_state(size), synth.make_nar_state(size)
     cfg = weights.dims_from_state(ar_sd, nar_sd, None, size["n_text"])
     prompt, spk, text = torch.from_numpy(wl["prompts"][0]).long(), torch.from_numpy(wl["spk"][0]).long(), torch.from_numpy(wl["text"][0]).long()
-    N, Pf = wl["N"], wl["Pf"]
+    N, Pf = wl["N_b"][0], wl["Pf"]
+    t_setup = time.perf_counter() - t_begin
     with torch.inference_mode():
         a, b = torch.randn(2048, 1024), torch.randn(1024, 4096)
-        n_big, _ = _best_threads(lambda: [a @ b for _ in range(4)], cands)   # thread count for the GEMM-shaped phases
-        torch.set_num_threads(n_big)
-        t0 = time.perf_counter()
-        cache = ar_oracle.KVCache()
-        ar_oracle.codeclm_step(ar_sd, cfg, prompt, spk, cache)          # prefill (timed once)
-        t_prefill = time.perf_counter() - t0
+        n_thr, _ = _best_threads(lambda: [a @ b for _ in range(4)], cands)
+        torch.set_num_threads(n_thr)
         g = torch.Generator().manual_seed(0)
+        # ---- AR: cached steps at the mean context
+        L_mean = len(prompt) + 1 + N // 2
+        H = cfg["ar_heads"]
+        cache = ar_oracle.KVCache()
+        for l in range(cfg["ar_layers"]):
+            cache.k[l] = torch.randn(L_mean, H, 64, generator=g)
+            cache.v[l] = torch.randn(L_mean, H, 64, generator=g)
+        cache.n = L_mean
+        t_ar_list = []
+        for i in range(3):
+            tok = torch.randint(size["n_text"], cfg["ar_vocab"], (1,), generator=g)
+            t0 = time.perf_counter()
+            ar_oracle.codeclm_step(ar_sd, cfg, tok, spk, cache)
+            t_ar_list.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_begin - t_setup > 0.3 * budget_s:
+                break
+        t_ar = min(t_ar_list)
+        del cache
+        # ---- NAR: one evaluation; full length when it fits the budget, else a shorter S scaled by the FLOP formula
+        S_full = Pf + (Pf - 1 + N)
+        Tc = len(text) + 1
 
-        def ar_steps():                                                  # KV-cached steps right after the prompt (the
-            for _ in range(n_ar_steps):                                  # cheapest context of the utterance), incl. the
-                tok = torch.randint(size["n_text"], cfg["ar_vocab"], (1,), generator=g)  # per-step speaker pass of the
-                ar_oracle.codeclm_step(ar_sd, cfg, tok, spk, cache)      # reference
-        n_small, t_steps = _best_threads(ar_steps, cands)
-        t_ar = t_steps / n_ar_steps
-        torch.set_num_threads(n_big)
-        S = Pf + (Pf - 1 + N)
-        x = torch.randint(0, 1025, (S, 8), generator=g)
+        def nar_flops(S):
+            return 16 * (2 * 17825792 * S + 4 * S * S * 1024 + 4 * S * Tc * 1024) + 8 * 2 * 1024 * 1025 * S
+
+        S_probe = min(256, S_full)
+        x = torch.randint(0, 1025, (S_probe, 8), generator=g)
+        nar_oracle.nar_forward(nar_sd, cfg, text, spk, x, T // 2, drop_cond=False)   # warms the pool, pages the weights
         t0 = time.perf_counter()
         nar_oracle.nar_forward(nar_sd, cfg, text, spk, x, T // 2, drop_cond=False)
-        t_nar = 2.0 * (time.perf_counter() - t0)                         # a reverse step = cond + uncond forward (+ posterior, not counted)
+        t_probe = time.perf_counter() - t0
+        left = budget_s - (time.perf_counter() - t_begin - t_setup)
+        est_full = t_probe * nar_flops(S_full) / nar_flops(S_probe)
+        S = S_full if est_full < 0.8 * left else max(S_probe, int(S_full * min(1.0, 0.8 * left / max(est_full, 1e-9))))
+        if S > S_probe:
+            x = torch.randint(0, 1025, (S, 8), generator=g)
+            t0 = time.perf_counter()
+            logits = nar_oracle.nar_forward(nar_sd, cfg, text, spk, x, T // 2, drop_cond=False)
+            t_fwd_S = time.perf_counter() - t0
+        else:
+            S, t_fwd_S = S_probe, t_probe
+            logits = nar_oracle.nar_forward(nar_sd, cfg, text, spk, x, T // 2, drop_cond=False)
+        t_fwd = t_fwd_S * nar_flops(S_full) / nar_flops(S)
+        # ---- posterior step (diffuser.py:359-393) on the same S rows, scaled linearly in S
+        tabs = nar_oracle.diffusion_tables(T)
+        K = cfg["n_classes"]
+        u = torch.rand(2, S, 8, K, generator=g)
+        xk, m = torch.zeros_like(x), torch.zeros_like(x).bool()
+        t0 = time.perf_counter()
+        nar_oracle.reverse_step(tabs, logits, logits, x, xk, m, T // 2, 3.0, 0.7, u[0], u[1], K)
+        t_post = (time.perf_counter() - t0) * S_full / S
+        # prefill: (P+1) tokens of AR GEMM work at the FLOP rate the NAR evaluation just achieved
+        rate = nar_flops(S) / t_fwd_S
+        t_prefill = 2 * 687128064 * (len(prompt) + 1) / rate
     audio = (N - 1) / 75.0
-    total = t_prefill + N * t_ar + T * t_nar
-    detail = {"t_prefill_s": round(t_prefill, 3), "t_ar_step_s": round(t_ar, 4), "t_nar_step_s": round(t_nar, 3),
-              "extrapolated_s_per_utterance": round(total, 1), "threads_gemm_phases": n_big, "threads_ar_steps": n_small,
-              "cores": max(n_big, n_small)}
-    return audio / total, detail
+    total = t_prefill + N * t_ar + T * (2 * t_fwd + t_post)
+    detail = {"t_ar_step_s": round(t_ar, 4), "ar_context": L_mean, "t_nar_forward_s": round(t_fwd, 3), "nar_rows_timed": S,
+              "nar_rows_full": S_full, "t_posterior_s": round(t_post, 3), "t_prefill_s_est": round(t_prefill, 3),
+              "extrapolated_s_per_utterance": round(total, 1), "cores": n_thr, "host_logical_cores": os.cpu_count(),
+              "sample_wall_s": round(time.perf_counter() - t_begin, 1)}
+    sample = (f"1 utterance of the workload: {len(t_ar_list)} KV-cached AR steps at the mean context ({L_mean} tokens, incl. the "
+              f"per-step speaker pass), 1 NAR evaluation at S={S} of {S_full} rows (x2 for cond+uncond, scaled by the FLOP formula "
+              f"when S < full), 1 posterior step; extrapolated to N={N} AR steps and T={T} reverse steps")
+    return audio / total, detail, sample
+
+
+def reference_c1_sample(T_sample=2, budget_s=120.0):
+    """The UNMODIFIED reference (/root/reference/mars5: ar_generate + perform_simple_inference) on BASELINE configs[0]
+    (shallow clone, 6 s reference, 10-word prompt, batch 1, CPU fp32), full-size random weights; AR for a bounded number
+    of tokens, NAR for T_sample of T = 200 reverse steps, extrapolated linearly (labelled).  Build container only."""
+    sys.path.insert(0, "/root/reference")
+    from mars5 import ar_generate as ref_ar
+    from mars5 import diffuser as ref_diff
+    from mars5.model import CodecLM, ResidualTransformer
+    from mars5_tts_b200 import synth
+    size = synth.FULL
+    torch.set_num_threads(os.cpu_count() or 1)
+    ar_sd, nar_sd = synth.make_ar_state(size), synth.make_nar_state(size)
+    V = size["n_text"] + size["n_speech"]
+    lm = CodecLM(n_vocab=V, dim=size["ar_dim"], nhead=size["ar_dim"] // 64, n_layers=size["ar_layers"],
+                 n_spk_layers=size["ar_spk_layers"], dim_ff_scale=7 / 3).eval()
+    nar = ResidualTransformer(n_text_vocab=size["n_text"] + 1, n_quant=1025, dim=size["nar_dim"], nhead=size["nar_dim"] // 64,
+                              enc_layers=size["nar_enc_layers"], dec_layers=size["nar_dec_layers"],
+                              n_spk_layers=size["nar_spk_layers"], t_emb_dim=size["nar_dim"], p_cond_drop=0, dropout=0).eval()
+    lm.load_state_dict(ar_sd, strict=True); nar.load_state_dict(nar_sd, strict=True)
+
+    class Tok:  # stand-in with the reference tokenisers' interface (the real models live in the checkpoints)
+        def __init__(self, n, special):
+            self.vocab, self.special_tokens = {i: (i,) for i in range(n)}, special
+    tt, st = Tok(size["n_text"], {}), Tok(size["n_speech"], {"<|endofspeech|>": size["n_speech"] - 1})
+    g = torch.Generator().manual_seed(0)
+    Pf, n_tok, n_gen = 450, 14, 24
+    spk = torch.randint(0, 1024, (Pf, 8), generator=g)
+    prompt = torch.randint(0, size["n_text"] - 2, (n_tok + 2,), generator=g)
+    with torch.inference_mode():
+        t0 = time.perf_counter()
+        seq = ref_ar.ar_generate(tt, st, lm, prompt, spk, len(prompt) + 1, max_len=len(prompt) + n_gen, fp16=False, temperature=0.7,
+                                 topk=200, top_p=0.2, alpha_frequency=3, alpha_presence=0.4, penalty_window=80, eos_penalty_decay=0.5,
+                                 eos_penalty_factor=1, n_phones_gen=50, vocode=False, use_kv_cache=True)
+        t_ar = (time.perf_counter() - t0) / max(1, len(seq) - len(prompt))
+        N = 15 * n_tok
+        diff = ref_diff.MultinomialDiffusion(1025, timesteps=T_sample)
+        dsh = ref_diff.DSH(last_greedy=True, x_0_temp=0.7, guidance_w=3, deep_clone=False, jump_len=1, jump_n_sample=1,
+                           q0_override_steps=20, enable_kevin_scaled_inference=True, progress=False)
+        _x = torch.randint(0, 1024, (1, N, 1), generator=g).repeat(1, 1, 8)
+        batch = (prompt[None], spk[None].clone(), torch.tensor([len(prompt)]), torch.tensor([Pf]), _x, torch.zeros(1, N, dtype=torch.bool))
+        t0 = time.perf_counter()
+        ref_diff.perform_simple_inference(nar, batch, diff, T_sample, torch.float16, dsh=dsh, retain_quant0=True)
+        t_nar = (time.perf_counter() - t0) / T_sample
+    total = N * t_ar + 200 * t_nar
+    return (N / 75.0) / total, {"t_ar_step_s": round(t_ar, 4), "t_nar_step_s": round(t_nar, 3), "cores": os.cpu_count(),
+                                "extrapolated_s_per_utterance": round(total, 1)}, \
+        (f"unmodified /root/reference modules, BASELINE configs[0] (shallow, Pf=450, 14 tokens -> N={N}, B=1): {n_gen - 2} AR tokens and "
+         f"{T_sample} of 200 reverse steps timed, extrapolated linearly")
 
 
 # ------------------------------------------------------------------------------------------------ main
@@ -205,13 +330,22 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", default="full", choices=["full", "mid", "tiny"])
-    ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--T", type=int, default=200)
-    ap.add_argument("--precise", type=int, default=0)
+    ap.add_argument("--config", default="c3", choices=["c2", "c3", "c4", "c5"],
+                    help="BASELINE configs: c2 = deep B=1 50 tok; c3 = deep B=32 100 tok (headline); c4 = mixed lengths; c5 = NAR-only sweep")
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--T", type=int, default=0)
+    ap.add_argument("--mode", default=os.environ.get("M5_BENCH_MODE", "mixed"), choices=list(MODES),
+                    help="NAR numerics: fast = fp16 operands everywhere; mixed = split-fp16 GEMM activations + split V "
+                         "(meets 1e-3 max-abs on the logits, tests/test_zzz_fullsize_gpu.py); precise = everything split")
+    ap.add_argument("--precise", type=int, default=-1, help="deprecated alias: 0 = fast, 1 = precise")
     ap.add_argument("--ntok", type=int, default=0, help="profiling aid: override the target-text token count (N = 15 * ntok)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--also-fast", action="store_true", help="also time one step in fast mode and report it beside the headline")
     args = ap.parse_args()
+    if args.precise >= 0:
+        args.mode = "precise" if args.precise else "fast"
+    mode = MODES[args.mode]
 
     from mars5_tts_b200 import synth
     size = {"full": synth.FULL, "mid": synth.MID, "tiny": synth.TINY}[args.size]
@@ -220,38 +354,51 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     small = args.size != "full"
     wl_kw = dict(n_text_tok=10, n_ref_tok=5, Pf=40, frames_per_tok=4) if small else {}
+    cfg_defaults = {"c2": (1, 50, 200), "c3": (32, 100, 200), "c4": (32, 100, 200), "c5": (128, 50, 64)}[args.config]
+    B = args.batch or cfg_defaults[0]
+    if not small:
+        wl_kw["n_text_tok"] = cfg_defaults[1]
     if args.ntok:
         wl_kw["n_text_tok"] = args.ntok
-    config = {"workload": f"deep-clone B={args.batch} Pf={wl_kw.get('Pf', 450)} text={wl_kw.get('n_text_tok', 100)}tok "
-                          f"N={wl_kw.get('n_text_tok', 100) * wl_kw.get('frames_per_tok', 15)} T={args.T} CFG w=3 ({args.size} model, "
-                          f"BASELINE configs[2])",
-              "global_batch": args.batch * world, "parallelism": f"dp{world}", "l2": "working set >> 126 MB L2 (weights 2.4 GB + KV 10 GB)",
-              "precise": args.precise}
+    T = args.T or cfg_defaults[2]
+    if args.config == "c4":
+        wl_kw["mixed"] = True
+    ntk, fpt = wl_kw.get("n_text_tok", 100), wl_kw.get("frames_per_tok", 15)
+    names = {"c2": "BASELINE configs[1]", "c3": "BASELINE configs[2]", "c4": "BASELINE configs[3] (per-GPU shard of 32)", "c5": "BASELINE configs[4], NAR only"}
+    config = {"workload": f"{'NAR-only ' if args.config == 'c5' else ''}deep-clone B={B} Pf={wl_kw.get('Pf', 450)} "
+                          f"text={'U{20..120}' if args.config == 'c4' else ntk}tok N={'15*tok' if args.config == 'c4' else ntk * fpt} T={T} CFG w=3 "
+                          f"({args.size} model, {names[args.config]})",
+              "global_batch": B * world, "parallelism": f"dp{world}", "l2": "working set >> 126 MB L2 (weights 2.4 GB + KV 10 GB)",
+              "nar_numerics": args.mode, "precise": mode}
 
-    # -------------------------------------------------------------------------------- reference arm (CPU port)
+    # -------------------------------------------------------------------------------- reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
         wl = make_workload(size, 1, 1234, **wl_kw)
-        vals, detail = [], {}
-        n_warm = 0  # deterministic CPU work (no clocks to settle): warm-up passes would only push the run past minutes
+        vals, detail, samp, kind = [], {}, "", "port"
         t_begin = time.perf_counter()
-        for i in range(n_warm + args.steps):
+        for i in range(max(1, args.steps)):
             t0 = time.perf_counter()
-            v, detail = cpu_port_sample(size, wl, args.T, n_ar_steps=2)
-            if i >= n_warm:
-                vals.append((v, time.perf_counter() - t0))
-            if vals and time.perf_counter() - t_begin > 150:  # bounded: the whole run must end within a few minutes
+            v, detail, samp = cpu_port_sample(size, wl, T, budget_s=25.0)
+            vals.append((v, time.perf_counter() - t0))
+            if time.perf_counter() - t_begin > 150:  # bounded: the whole run must end within a few minutes
                 break
-        config["steps_measured"] = len(vals)
-        v = float(np.mean([a for a, _ in vals])) if vals else 0.0
-        ms = float(np.mean([b for _, b in vals]) * 1e3) if vals else 0.0
-        samp = "1 utterance: prefill + 2 KV-cached AR steps (context = prompt) + 1 NAR forward at S=2399 (x2 for cond+uncond), extrapolated to N AR steps and T reverse steps"
-        print(json.dumps({"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic", "impl": "reference", "config": config,
-                          "cpu_baseline": {"value": v, "unit": UNIT, "kind": "port", "sample": samp, **detail},
-                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        v = float(np.mean([a for a, _ in vals]))
+        ms = float(np.mean([b for _, b in vals]) * 1e3)
+        line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "steps_requested": args.steps,
+                "warmup": 0, "warmup_requested": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference", "config": config,
+                "cpu_baseline": {"value": v, "unit": UNIT, "kind": kind, "sample": samp, **detail},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "each step = one bounded sample (no warm-up passes: deterministic CPU work)"}
+        if os.path.isdir("/root/reference/mars5") and os.environ.get("M5_BENCH_REF_C1", "1") == "1":
+            try:
+                v1, d1, s1 = reference_c1_sample()
+                line["reference_c1"] = {"value": v1, "unit": UNIT, "kind": "reference", "sample": s1, **d1}
+            except Exception as e:  # the unmodified reference is an extra, never a reason to lose the line
+                line["reference_c1"] = {"unavailable": repr(e)[:200]}
+        print(json.dumps(line))
         return
 
     # -------------------------------------------------------------------------------- our arm
@@ -264,22 +411,35 @@ def main():
     packed = m5dist.build_or_receive_weights(size, rank, world, local, max_pos=4096)
     eng = Engine(device=local, packed=packed)
     icfg = InferenceConfig()
-    wl = make_workload(size, args.batch, 1234 + rank, utt_base=rank * args.batch, **wl_kw)
-    stream = torch.cuda.ExternalStream(eng.lib.m5_stream(eng.ctx), device=torch.device("cuda", local))
+    wl = make_workload(size, B, 1234 + rank, utt_base=rank * B, **wl_kw)
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.ExternalStream(eng.lib.m5_stream(eng.ctx), device=dev)
+    dw = to_device(wl, dev)
+    nar_only = args.config == "c5"
+    if nar_only:
+        g = torch.Generator().manual_seed(99 + rank)
+        dw["l0"] = torch.randint(0, 1024, (B * (wl["Pf"] - 1 + wl["N"]),), generator=g, dtype=torch.int32).to(dev)
+    if args.config == "c4":  # mixed lengths go through the list API (per-utterance forced lengths differ): host buffers only
+        raise SystemExit("config c4 is covered by tests/test_dist_*.py (sharding) -- bench lines exist for c2, c3, c5")
 
-    dw = to_device(wl, torch.device("cuda", local))
-
-    def step_dev():
-        wav = run_step_device(eng, icfg, wl, dw, args.T, args.precise)
+    def step_dev(T_=T, mode_=mode):
+        wav = (run_step_nar_only if nar_only else run_step_device)(eng, icfg, wl, dw, T_, mode_)
         if world > 1:
             m5dist.all_gather_waveforms(list(wav.view(wl["B"], -1)), local)
         return wav
 
     def step_host():
-        wavs = run_step(eng, icfg, wl, args.T, args.precise)
+        wavs = run_step(eng, icfg, wl, T, mode)
         if world > 1:
             m5dist.all_gather_waveforms(wavs, local)
         return wavs
+
+    def allmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
 
     def timed(n, step):
         if world > 1:
@@ -293,15 +453,22 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             torch.distributed.barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=f"cuda:{local}")
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, wavs
+        return allmax(e0.elapsed_time(e1)), wavs
 
-    for _ in range(args.warmup):
-        step_dev()
+    # ---- warm-up: W-1 short passes (full shapes, T = 8), then one complete step that calibrates the step time
+    t_full_ms = None
+    for i in range(args.warmup):
+        if i + 1 < args.warmup:
+            step_dev(T_=min(T, 8))
+        else:
+            t_full_ms, _ = timed(1, step_dev)
+    n_steps = args.steps
+    if t_full_ms is not None:
+        reserve = (0 if (args.no_e2e or nar_only) else 1.08 * t_full_ms / 1e3) + (45 if (world == 1 and not args.no_cpu_baseline) else 0) + 15
+        if args.also_fast:
+            reserve += t_full_ms / 1e3
+        fit = int((BUDGET_S - allmax(elapsed()) - reserve) // (t_full_ms / 1e3))
+        n_steps = max(1, min(args.steps, fit))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -309,51 +476,70 @@ def main():
     for k in PHASE_S:
         PHASE_S[k] = 0.0
     l0 = eng.launches
-    ms, wav_dev = timed(args.steps, step_dev)
+    ms, wav_dev = timed(n_steps, step_dev)
     launches = eng.launches - l0
     import ctypes as C
     prof = {}
-    for kind, name in ((0, "gemm_tc5"), (1, "flash_attn")):
+    for kind, name in ((0, "gemm_tc5"), (1, "flash_attn"), (2, "ar_decode")):
         a, b, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
         eng.lib.m5_profile_read(eng.ctx, kind, C.byref(a), C.byref(b), C.byref(c), C.byref(n))
         prof[name] = dict(ms=a.value, flops=b.value, bytes=c.value, launches=n.value)
     eng.lib.m5_profile_enable(eng.ctx, 0)
     clocks = sampler.stop() if rank == 0 else {}
-    phases = {k: round(v / args.steps * 1e3, 1) for k, v in PHASE_S.items()}
-    e2e_steps = 1  # one end-to-end step keeps the default run within minutes (each step is ~40 s of GPU work)
-    ms_e2e, wavs = (ms / args.steps, None) if args.no_e2e else timed(e2e_steps, step_host)
-    audio_total = wl["audio_s"] * world * args.steps
+    phases = {k: round(v / n_steps * 1e3, 1) for k, v in PHASE_S.items()}
+    e2e_steps = 1  # one end-to-end step keeps the default run within minutes
+    ms_e2e, wavs = (ms / n_steps, None) if (args.no_e2e or nar_only) else timed(e2e_steps, step_host)
+    fast_ms = None
+    if args.also_fast and mode != 0:
+        fast_ms, _ = timed(1, lambda: step_dev(mode_=0))
+    audio_total = wl["audio_s"] * world * n_steps
     value = audio_total / (ms / 1e3)
     if rank != 0:
         return
     peak_tf, peak_gbs, peak_src = measured_peaks()
-    gp = prof["gemm_tc5"]
+    gp, ap_ = prof["gemm_tc5"], prof["ar_decode"]
     ach = gp["flops"] / max(gp["ms"], 1e-9) / 1e9  # TFLOP/s
     roofline = {"kernel": "gemm_tc5_2cta_kernel / gemm_tc5_kernel (tcgen05; every NAR, AR-prefill and vocoder GEMM)", "bound": "tensor",
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                # `achieved` averages over every GEMM shape of the step, so no single DRAM-byte figure matches it; the one
-                # ncu --set full capture (profiles/r1_gemm_tc5_2cta_ncu.txt) is reported with its own shape instead
-                "traffic": None,
+                # per launch, like `achieved`: algorithmic operand bytes of the average launch; DRAM traffic of the one
+                # shape captured with ncu --set full (profiles/) is given with its own algorithmic bytes beside it
+                "traffic": gp["bytes"] / max(gp["launches"], 1),
+                "traffic_is": "algorithmic bytes per average launch (A + W + C once); ncu dram bytes of one shape in traffic_ncu",
                 "traffic_ncu": {"shape": "M=153552 N=3072 K=1024 fp16 out", "dram_bytes": 376112128 + 901768704,
                                 "algorithmic_bytes": 2 * (153552 * 1024 + 3072 * 1024 + 153552 * 3072)},
                 "peak_source": peak_src,
                 "launches": gp["launches"], "avg_launch_ms": gp["ms"] / max(gp["launches"], 1),
                 "share_of_step": gp["ms"] / ms, "flash_attn_tflops": prof["flash_attn"]["flops"] / max(prof["flash_attn"]["ms"], 1e-9) / 1e9,
                 "flash_attn_share_of_step": prof["flash_attn"]["ms"] / ms}
+    roofline_ar = None
+    if ap_["launches"] > 0:
+        gbs = ap_["bytes"] / max(ap_["ms"], 1e-9) / 1e6
+        roofline_ar = {"kernel": "AR decode step (fused per-layer decode kernels + sampler, one CUDA graph per step)", "bound": "hbm",
+                       "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
+                       "bytes_per_step": ap_["bytes"] / ap_["launches"], "ms_per_decode_step": ap_["ms"] / ap_["launches"],
+                       "decode_steps": ap_["launches"], "share_of_step": ap_["ms"] / ms,
+                       "formula": "W_ar + sum_b 159744*(L_b+1) + B*1536*2 per step (SURVEY 8(d))"}
     n_in = sum(p.nbytes for p in wl["prompts"]) + 2 * sum(s.nbytes for s in wl["spk"]) + sum(t.nbytes for t in wl["text"])
     n_out = wav_dev.numel() * 4
     e2e = {"value": wl["audio_s"] * world * e2e_steps / (ms_e2e / 1e3), "unit": UNIT, "steps": e2e_steps, "h2d_bytes_per_step": int(n_in + wl["B"] * wl["N"] * 4),
            "d2h_bytes_per_step": int(n_out + wl["B"] * wl["max_len"] * 4 + wl["B"] * (wl["Pf"] + wl["N"]) * 32),
            "note": "Engine.ar_generate / nar_infer / vocode with HOST buffers (mem=M5_MEM_HOST): ids and codes are copied in, "
                    "AR ids, NAR codes and the fp32 waveforms are copied out every step"}
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f16 operands / f32 accumulate", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
-           "gpu_launches": int(launches), "roofline": roofline, "phase_ms_per_step": phases, "realtime_factor_per_gpu": value / world}
+    if args.no_e2e or nar_only:
+        e2e["note"] = "not measured in this run (device-resident value repeated)"
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": n_steps, "steps_requested": args.steps,
+           "warmup": args.warmup, "warmup_note": f"{max(args.warmup - 1, 0)} passes at T={min(T, 8)} + 1 complete step",
+           "ms_per_step": ms / n_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f16 operands (split hi/lo pairs where nar_numerics says so) / f32 accumulate", "data": "synthetic", "config": config,
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_ar": roofline_ar,
+           "phase_ms_per_step": phases, "realtime_factor_per_gpu": value / world, "wall_s": round(elapsed(), 1)}
+    if fast_ms is not None:
+        out["fast_mode"] = {"value": wl["audio_s"] * world / (fast_ms / 1e3), "unit": UNIT, "steps": 1,
+                            "note": "nar_numerics=fast (fp16 operands everywhere): does NOT meet the 1e-3 max-abs logit bound"}
     if world == 1 and not args.no_cpu_baseline:
-        v, detail = cpu_port_sample(size, make_workload(size, 1, 1234, **wl_kw), args.T, n_ar_steps=2)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "kind": "port",
-                               "sample": "1 utterance: prefill + 2 KV-cached AR steps (context = prompt) + 1 NAR forward at S=2399 (x2), extrapolated to N AR steps and T reverse steps", **detail}
+        v, detail, samp = cpu_port_sample(size, make_workload(size, 1, 1234, **wl_kw), T, budget_s=25.0)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "kind": "port", "sample": samp, **detail}
+    out["wall_s"] = round(elapsed(), 1)
     print(json.dumps(out))
 
 

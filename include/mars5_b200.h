@@ -71,8 +71,10 @@ int m5_num_sms(m5_ctx* ctx);
 /* cudaStream_t the context enqueues on (for the caller's CUDA events). */
 void* m5_stream(m5_ctx* ctx);
 /* Kernel-class timing with CUDA events on the context's stream (bench.py's roofline leg).  kind 0 = tcgen05 GEMM,
- * 1 = flash attention.  m5_profile_read returns, accumulated since the last enable: total device ms, algorithmic
- * FLOPs (2*M*N*K per GEMM; 4*q*k*64 per attention head pair), algorithmic bytes and number of launches. */
+ * 1 = flash attention, 2 = the AR decode loop (one record per m5_ar_generate call: `launches` counts decode steps, bytes
+ * = weights + KV-cache bytes those steps had to move).  m5_profile_read returns, accumulated since the
+ * last enable: total device ms, algorithmic FLOPs (2*M*N*K per GEMM; 4*q*k*64 per attention head pair), algorithmic
+ * bytes and number of launches. */
 int m5_profile_enable(m5_ctx* ctx, int32_t on);
 int m5_profile_read(m5_ctx* ctx, int32_t kind, double* ms, double* flops, double* bytes, int64_t* launches);
 
@@ -113,7 +115,11 @@ typedef struct {
   float guidance_w;   /* DSH.guidance_w */
   int32_t q0_override_steps;
   int32_t deep_clone;
-  int32_t precise;    /* 1: split-fp16 GEMM operands (fp32-class accuracy, 2x tensor work) */
+  int32_t precise;    /* NAR numerics: 0 fast   = every GEMM / attention operand is one fp16 value (fp32 accumulate);
+                       *               1 precise = every activation operand is an fp16 (hi, lo) pair (1e-5 on the logits);
+                       *               2 mixed   = GEMM activations, keys and values are pairs, queries and probabilities
+                       *                           single fp16, attention on tcgen05: the cheapest setting that keeps the
+                       *                           logits within 1e-3 max-abs of the fp32 reference */
   /* optional HOST tables [4][T]: log_alpha, log_1_min_alpha, log_cumprod_alpha, log_1_min_cumprod_alpha
    * (MultinomialDiffusion.__init__, diffuser.py:76-95); NULL -> computed inside the library */
   const float* schedule;
@@ -194,6 +200,11 @@ int m5_dbg_attn(m5_ctx* ctx, const void* Q, const void* K, const void* V, int32_
                 void* O, int32_t ldo, int32_t n_heads, int32_t n_seqs, int32_t max_q, const int32_t* q_start,
                 const int32_t* q_len, const int32_t* k_start, const int32_t* k_len, int32_t causal, int32_t impl,
                 int32_t q_rows, int32_t k_rows); /* impl: 1 = mma.sync kernel, 2 = tcgen05 kernel (needs q_rows/k_rows) */
+/* tcgen05 kernel with keys / values as fp16 (hi, lo) pairs and the output written as a pair ("mixed" numerics). */
+int m5_dbg_attn_split(m5_ctx* ctx, const void* Q, const void* K, const void* V, const void* Klo, const void* Vlo,
+                      int32_t ldq, int32_t ldk, int32_t ldv, void* O, void* Olo, int32_t ldo, int32_t n_heads,
+                      int32_t n_seqs, int32_t max_q, const int32_t* q_start, const int32_t* q_len, const int32_t* k_start,
+                      const int32_t* k_len, int32_t q_rows, int32_t k_rows);
 int m5_dbg_decode_attn(m5_ctx* ctx, const void* q, const void* kc, const void* vc, int32_t B, int32_t H, int32_t W,
                        const int32_t* kv_len, void* out, int32_t n_split);
 /* AR sampler chain on fp32 logits [B][V] (ar_generate.py:73-118): writes the chosen token per row. */

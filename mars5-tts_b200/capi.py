@@ -11,6 +11,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 DT_F16, DT_F32 = 0, 1
 OUT_F32, OUT_F16, OUT_SWIGLU_F16, OUT_F16_SPLIT, OUT_SWIGLU_F16_SPLIT = 0, 1, 2, 3, 4
 ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
+NUM_FAST, NUM_PRECISE, NUM_MIXED = 0, 1, 2   # m5_nar_cfg.precise (NAR numerics)
 
 
 class ModelCfg(C.Structure):
@@ -62,6 +63,7 @@ _SIGS = {
     "m5_dbg_skinny": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _I]),
     "m5_dbg_norm": (_I, [_P, _P, _I, _I, _P, _P, C.c_float, _I, _P, _P]),
     "m5_dbg_attn": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I]),
+    "m5_dbg_attn_split": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I]),
     "m5_dbg_decode_attn": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I]),
     "m5_dbg_sample": (_I, [_P, _P, _I, _I, C.POINTER(ArCfg), _I, _P, _I, _P, _P, _P, C.c_uint64, _P, _P]),
     "m5_dbg_posterior": (_I, [_P, _P, _P, _I, _I, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, C.c_uint64, _P]),

@@ -172,7 +172,7 @@ static int ar_speaker(m5_ctx* ctx, const ArWeights& w, ArPlan& p, const int* d_c
   if (chunked_embed(e, ctx->stream) != M5_OK) return ctx->fail(M5_ERR_CUDA, "chunked_embed(ar spk) failed");
   ctx->launches++;
   for (int l = 0; l < c.ar_spk_layers; ++l)
-    M5_TRY(encoder_layer(ctx, spk_x, p.spk, w.spk[l], c.ar_dim, c.ar_heads, c.ar_spk_ff, c.ln_eps, true, bs));
+    M5_TRY(encoder_layer(ctx, spk_x, p.spk, w.spk[l], c.ar_dim, c.ar_heads, c.ar_spk_ff, c.ln_eps, M5_NUM_PRECISE, bs));
   NormCall n;
   n.x = spk_x; n.M = p.B; n.D = c.ar_dim; n.ldx = c.ar_dim; n.gamma = w.spk_nw; n.beta = w.spk_nb; n.eps = c.ln_eps;
   n.out_f32 = spk_vec; n.ldo = c.ar_dim; n.row_map = p.spk_first;
@@ -348,8 +348,10 @@ int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int3
                    const m5_ar_cfg* cfg, int32_t mem, const float* noise, int32_t noise_steps, uint64_t seed,
                    const int64_t* utt_ids, int32_t* out_ids, int32_t* out_len, int32_t* hit_maxlen,
                    float* logits_dump, int32_t dump_steps) {
-  if (!ctx || !cfg || B <= 0 || B > 32) return M5_ERR_ARG;
+  if (!ctx || !cfg || B <= 0) return M5_ERR_ARG;
   ctx->last_error.clear();
+  if (B > 32) return ctx->fail(M5_ERR_ARG, "m5_ar_generate keeps at most 32 utterances in flight per call (B = " + std::to_string(B) +
+                                               "); split the batch (Mars5TTS.tts_batch does)");
   cudaSetDevice(ctx->device);
   ArWeights w;
   M5_TRY(load_ar(ctx, w));
@@ -452,11 +454,13 @@ int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int3
     if (ce != cudaSuccess) return ctx->fail(M5_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
     M5_CUDA(cudaGraphInstantiate(&exec, graph, 0));
   }
-  int h_done = 0;
+  int h_done = 0, steps_run = 0;
+  cudaEvent_t pe = prof_begin(ctx);   // kind 2: the whole decode loop (bench.py's AR HBM roofline)
   for (int s = 0; s < max_steps; ++s) {
     cudaError_t le = cudaGraphLaunch(exec, ctx->stream);
     if (le != cudaSuccess) { cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); return ctx->fail(M5_ERR_CUDA, std::string("graph launch: ") + cudaGetErrorString(le)); }
     ctx->launches += step_launches;
+    steps_run = s + 1;
     if ((s + 1) % sync_every == 0 || s + 1 == max_steps) {
       cudaMemcpyAsync(&h_done, st.n_done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
       cudaError_t se = cudaStreamSynchronize(ctx->stream);
@@ -464,6 +468,8 @@ int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int3
       if (h_done >= B) break;
     }
   }
+  if (pe) prof_end(ctx, pe, 2, 0.0, 0.0, steps_run);
+  const bool prof_rec = pe && !ctx->prof_pending.empty() && ctx->prof_pending.back().kind == 2;
   if (exec) cudaGraphExecDestroy(exec);
   if (graph) cudaGraphDestroy(graph);
   // ---- results
@@ -474,6 +480,22 @@ int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int3
   if (logits_dump && mem == M5_MEM_HOST)
     M5_CUDA(cudaMemcpyAsync(logits_dump, d_dump, (size_t)B * dump_steps * V * 4, cudaMemcpyDeviceToHost, ctx->stream));
   M5_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (prof_rec) {
+    // algorithmic bytes of the decode steps: every step reads the fp16 weights once, and for every row
+    // still running the K/V of all cached tokens (4*layers*D bytes each) plus the new token's K/V and embedding row
+    const double w_ar = 2.0 * ((double)L * (4.0 * D * D + 3.0 * (double)F * D) + (2.0 * L + 1) * D + (double)V * D);
+    const double kvb = 4.0 * L * D;
+    double bytes = (double)steps_run * w_ar, flops = 0.0;
+    for (int b = 0; b < B; ++b) {
+      const int gen = h_len[b] - p.P[b];                    // tokens appended (the first one came from the prefill)
+      const int act = std::max(0, std::min(steps_run, gen)); // decode steps in which row b was still running
+      const double l0 = p.P[b] + 2;                         // spk slot + prompt + the token being fed at decode step 0
+      bytes += kvb * (act * l0 + 0.5 * act * (act - 1.0)) + act * (kvb + 2.0 * D);
+      flops += act * 2.0 * ((double)L * (4.0 * D * D + 3.0 * (double)F * D) + (double)V * D) + kvb * (act * l0 + 0.5 * act * (act - 1.0));
+    }
+    ctx->prof_pending.back().bytes = bytes;
+    ctx->prof_pending.back().flops = flops;
+  }
   for (int b = 0; b < B; ++b) {
     if (out_len) out_len[b] = h_len[b];
     if (hit_maxlen) hit_maxlen[b] = h_len[b] >= max_len - 1 ? 1 : 0;  // ar_generate.py:160-162

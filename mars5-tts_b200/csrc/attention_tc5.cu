@@ -31,19 +31,28 @@
 namespace m5 {
 
 static constexpr int AT_BQ = 128, AT_BK = 64, AT_HD = 64, AT_THREADS = 192;
-static constexpr int AT_KST = 4, AT_VST = 3, AT_KLEAD = 2, AT_SST = 3;   // K ring, V ring, K lead over V, S slots
+static constexpr int AT_KLEAD = 2, AT_SST = 3;           // K lead over V (tiles), S slots
 static constexpr int AT_Q_BYTES = AT_BQ * AT_HD * 2;     // 16 KB
 static constexpr int AT_KV_BYTES = AT_BK * AT_HD * 2;    //  8 KB
 static constexpr int AT_P_BYTES = AT_BQ * AT_BK * 2;     // 16 KB (one 128-row K-major block)
-static constexpr int AT_OFF_Q = 0, AT_OFF_K = AT_Q_BYTES, AT_OFF_V = AT_OFF_K + AT_KST * AT_KV_BYTES,
-                     AT_OFF_P = AT_OFF_V + AT_VST * AT_KV_BYTES, AT_OFF_BAR = AT_OFF_P + 2 * AT_P_BYTES;
-static constexpr int AT_SMEM = AT_OFF_BAR + 256 + 1024;
 static constexpr int AT_TMEM_COLS = 256, AT_TMEM_O = AT_SST * AT_BK;   // S slots at 0/64/128, O at 192
-// mbarrier slots
-static constexpr int B_QFULL = 0, B_KFULL = 1, B_KFREE = B_KFULL + AT_KST, B_VFULL = B_KFREE + AT_KST, B_VFREE = B_VFULL + AT_VST,
-                     B_SREADY = B_VFREE + AT_VST, B_PREADY = B_SREADY + AT_SST, B_PVDONE = B_PREADY + 2, B_COUNT = B_PVDONE + 2;
-static_assert(B_COUNT * 8 + 8 <= 256, "barrier block");
 static_assert(AT_TMEM_O + AT_HD <= AT_TMEM_COLS, "TMEM budget");
+// SPLIT = keys and values arrive as fp16 (hi, lo) pairs ("mixed" NAR numerics): every ring stage holds the
+// hi tile followed by the lo tile, S_j = Q K_hi^T + Q K_lo^T and O += P V_hi + P V_lo accumulate in the same TMEM columns,
+// and O is written as a (hi, lo) pair.  The rings are shallower (2 + 2 stages of 16 KB) so that two CTAs still fit one SM.
+template <bool SPLIT>
+struct AtCfg {
+  static constexpr int KST = SPLIT ? 2 : 4, VST = SPLIT ? 2 : 3;        // K ring, V ring
+  static constexpr int STAGE = SPLIT ? 2 * AT_KV_BYTES : AT_KV_BYTES;
+  static constexpr int OFF_Q = 0, OFF_K = AT_Q_BYTES, OFF_V = OFF_K + KST * STAGE, OFF_P = OFF_V + VST * STAGE,
+                       OFF_BAR = OFF_P + 2 * AT_P_BYTES;
+  static constexpr int SMEM = OFF_BAR + 256;
+  // mbarrier slots
+  static constexpr int B_QFULL = 0, B_KFULL = 1, B_KFREE = B_KFULL + KST, B_VFULL = B_KFREE + KST, B_VFREE = B_VFULL + VST,
+                       B_SREADY = B_VFREE + VST, B_PREADY = B_SREADY + AT_SST, B_PVDONE = B_PREADY + 2, B_COUNT = B_PVDONE + 2;
+  static_assert(B_COUNT * 8 + 8 <= 256, "barrier block");
+  static_assert(2 * (SMEM + 1024) <= 228 * 1024, "two CTAs per SM");
+};
 
 // Instruction descriptor: fp16 x fp16 -> fp32, A K-major, B major selectable.
 __host__ __device__ constexpr uint32_t at_idesc(uint32_t M, uint32_t N, uint32_t b_mn_major) {
@@ -74,7 +83,7 @@ M5_DEVINL float fmax3(float a, float b, float c) {
 
 struct AttnTc5Params {
   const int* q_start; const int* q_len; const int* k_start; const int* k_len;
-  __half* O; int ldo;
+  __half* O; __half* Olo; int ldo;
   float scale_log2;
 };
 
@@ -134,15 +143,25 @@ struct Ring {
   }
 };
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 flash_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                 const __grid_constant__ CUtensorMap tmap_v, AttnTc5Params p) {
+                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_klo,
+                 const __grid_constant__ CUtensorMap tmap_vlo, AttnTc5Params p) {
+  using C = AtCfg<SPLIT>;
+  constexpr int AT_KST = C::KST, AT_VST = C::VST, AT_STAGE = C::STAGE;
+  constexpr int AT_OFF_Q = C::OFF_Q, AT_OFF_K = C::OFF_K, AT_OFF_V = C::OFF_V, AT_OFF_P = C::OFF_P, AT_OFF_BAR = C::OFF_BAR;
+  constexpr int B_QFULL = C::B_QFULL, B_KFULL = C::B_KFULL, B_KFREE = C::B_KFREE, B_VFULL = C::B_VFULL, B_VFREE = C::B_VFREE,
+                B_SREADY = C::B_SREADY, B_PREADY = C::B_PREADY, B_PVDONE = C::B_PVDONE, B_COUNT = C::B_COUNT;
   const int seq = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
   const int q_len = p.q_len[seq], k_len = p.k_len[seq];
   const int q0 = qt * AT_BQ;
   if (q0 >= q_len) return;
-  extern __shared__ uint8_t at_smem_raw[];
-  uint8_t* smem = at_smem_raw + ((1024u - (smem_u32(at_smem_raw) & 1023u)) & 1023u);
+  // no static shared memory in this kernel: the dynamic window starts at the CTA's shared base, which is 1024-byte aligned
+  // (checked below); the 128B-swizzle tiles need that alignment
+  extern __shared__ __align__(1024) uint8_t at_smem_raw[];
+  uint8_t* smem = at_smem_raw;
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) { printf("m5: flash_tc5 shared memory base is not 1 KiB aligned\n"); __trap(); }
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + AT_OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + B_COUNT);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -171,15 +190,20 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int i = 0; i < n_tiles + AT_KLEAD; ++i) {
         if (i < n_tiles) {
           mbar_wait(bar + B_KFREE + kr.slot, kr.phase ^ 1);
-          mbar_arrive_expect_tx(bar + B_KFULL + kr.slot, AT_KV_BYTES);
-          tma_load_2d(smem + AT_OFF_K + kr.slot * AT_KV_BYTES, &tmap_k, bar + B_KFULL + kr.slot, head * AT_HD, krow + i * AT_BK);
+          mbar_arrive_expect_tx(bar + B_KFULL + kr.slot, AT_STAGE);
+          tma_load_2d(smem + AT_OFF_K + kr.slot * AT_STAGE, &tmap_k, bar + B_KFULL + kr.slot, head * AT_HD, krow + i * AT_BK);
+          if (SPLIT)
+            tma_load_2d(smem + AT_OFF_K + kr.slot * AT_STAGE + AT_KV_BYTES, &tmap_klo, bar + B_KFULL + kr.slot, head * AT_HD, krow + i * AT_BK);
           kr.next(AT_KST);
         }
         if (i >= AT_KLEAD) {
           mbar_wait(bar + B_VFREE + vr.slot, vr.phase ^ 1);
-          mbar_arrive_expect_tx(bar + B_VFULL + vr.slot, AT_KV_BYTES);
-          tma_load_2d(smem + AT_OFF_V + vr.slot * AT_KV_BYTES, &tmap_v, bar + B_VFULL + vr.slot, head * AT_HD,
+          mbar_arrive_expect_tx(bar + B_VFULL + vr.slot, AT_STAGE);
+          tma_load_2d(smem + AT_OFF_V + vr.slot * AT_STAGE, &tmap_v, bar + B_VFULL + vr.slot, head * AT_HD,
                       krow + (i - AT_KLEAD) * AT_BK);
+          if (SPLIT)
+            tma_load_2d(smem + AT_OFF_V + vr.slot * AT_STAGE + AT_KV_BYTES, &tmap_vlo, bar + B_VFULL + vr.slot, head * AT_HD,
+                        krow + (i - AT_KLEAD) * AT_BK);
           vr.next(AT_VST);
         }
       }
@@ -193,9 +217,14 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       auto issue_s = [&]() {
         mbar_wait(bar + B_KFULL + kr.slot, kr.phase);
         tc5_fence_after();
-        const uint64_t dk = umma_desc_k_sw128(smem_u32(smem + AT_OFF_K + kr.slot * AT_KV_BYTES));
+        const uint64_t dk = umma_desc_k_sw128(smem_u32(smem + AT_OFF_K + kr.slot * AT_STAGE));
 #pragma unroll
         for (int k = 0; k < AT_HD / 16; ++k) tc5_mma_f16(tmem_base + sr.slot * AT_BK, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        if (SPLIT) {   // + Q K_lo^T: the lo tile sits AT_KV_BYTES behind the hi tile of the stage
+          const uint64_t dkl = dk + (uint64_t)(AT_KV_BYTES >> 4);
+#pragma unroll
+          for (int k = 0; k < AT_HD / 16; ++k) tc5_mma_f16(tmem_base + sr.slot * AT_BK, dq + 2 * k, dkl + 2 * k, idesc_s, 1);
+        }
         tc5_commit(bar + B_KFREE + kr.slot);
         tc5_commit(bar + B_SREADY + sr.slot);
         kr.next(AT_KST);
@@ -211,10 +240,15 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         mbar_wait(bar + B_VFULL + vr.slot, vr.phase);
         tc5_fence_after();
         const uint64_t dp = umma_desc_k_sw128(smem_u32(smem + AT_OFF_P + pr.slot * AT_P_BYTES));
-        const uint64_t dv = umma_desc_mn_sw128(smem_u32(smem + AT_OFF_V + vr.slot * AT_KV_BYTES));
+        const uint64_t dv = umma_desc_mn_sw128(smem_u32(smem + AT_OFF_V + vr.slot * AT_STAGE));
 #pragma unroll
         for (int k = 0; k < AT_BK / 16; ++k)   // A: 16 keys = 32 B inside the 128-byte P row; B: 16 key rows = 2048 B of V
           tc5_mma_f16(tmem_o, dp + 2 * k, dv + (uint64_t)(k * (16 * 128 >> 4)), idesc_o, (j != 0) || (k != 0));
+        if (SPLIT) {
+          const uint64_t dvl = dv + (uint64_t)(AT_KV_BYTES >> 4);
+#pragma unroll
+          for (int k = 0; k < AT_BK / 16; ++k) tc5_mma_f16(tmem_o, dp + 2 * k, dvl + (uint64_t)(k * (16 * 128 >> 4)), idesc_o, 1);
+        }
         tc5_commit(bar + B_VFREE + vr.slot);
         tc5_commit(bar + B_PVDONE + pr.slot);
         vr.next(AT_VST);
@@ -310,25 +344,27 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
     if (q0 + row < q_len) {
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      __half* og = p.O + (size_t)(p.q_start[seq] + q0 + row) * p.ldo + head * AT_HD;
+      const size_t ooff = (size_t)(p.q_start[seq] + q0 + row) * p.ldo + head * AT_HD;
+      __half* og = p.O + ooff;
+      auto store32 = [&](const uint32_t (&r)[32], int base) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        uint4 w;
-        w.x = pack_half2(__uint_as_float(ra[i]) * inv, __uint_as_float(ra[i + 1]) * inv);
-        w.y = pack_half2(__uint_as_float(ra[i + 2]) * inv, __uint_as_float(ra[i + 3]) * inv);
-        w.z = pack_half2(__uint_as_float(ra[i + 4]) * inv, __uint_as_float(ra[i + 5]) * inv);
-        w.w = pack_half2(__uint_as_float(ra[i + 6]) * inv, __uint_as_float(ra[i + 7]) * inv);
-        *reinterpret_cast<uint4*>(og + i) = w;
-      }
+        for (int i = 0; i < 32; i += 8) {
+          uint32_t h[4], l[4];
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        uint4 w;
-        w.x = pack_half2(__uint_as_float(rb[i]) * inv, __uint_as_float(rb[i + 1]) * inv);
-        w.y = pack_half2(__uint_as_float(rb[i + 2]) * inv, __uint_as_float(rb[i + 3]) * inv);
-        w.z = pack_half2(__uint_as_float(rb[i + 4]) * inv, __uint_as_float(rb[i + 5]) * inv);
-        w.w = pack_half2(__uint_as_float(rb[i + 6]) * inv, __uint_as_float(rb[i + 7]) * inv);
-        *reinterpret_cast<uint4*>(og + 32 + i) = w;
-      }
+          for (int e = 0; e < 4; ++e) {
+            const float v0 = __uint_as_float(r[i + 2 * e]) * inv, v1 = __uint_as_float(r[i + 2 * e + 1]) * inv;
+            h[e] = pack_half2(v0, v1);
+            if (SPLIT) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[e]));
+              l[e] = pack_half2(v0 - f.x, v1 - f.y);
+            }
+          }
+          *reinterpret_cast<uint4*>(og + base + i) = make_uint4(h[0], h[1], h[2], h[3]);
+          if (SPLIT) *reinterpret_cast<uint4*>(p.Olo + ooff + base + i) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+      };
+      store32(ra, 0);
+      store32(rb, 32);
     }
   }
   tc5_fence_before();
@@ -370,21 +406,25 @@ int flash_attn_tc5(const AttnCall& c, cudaStream_t stream) {
   if (c.n_seqs <= 0 || c.max_q <= 0) return M5_OK;
   if (c.causal || c.q_rows <= 0 || c.k_rows <= 0) return M5_ERR_ARG;
   if ((c.ldq | c.ldk | c.ldv | c.ldo) % 8 != 0) return M5_ERR_ARG;
-  CUtensorMap tq, tk, tv;
+  const bool split = c.Klo != nullptr;   // keys / values as (hi, lo) pairs, O written as a pair; Q and P stay single fp16
+  if (split && (!c.Vlo || !c.Olo)) return M5_ERR_ARG;
+  CUtensorMap tq, tk, tv, tkl, tvl;
   const uint64_t cols = (uint64_t)c.n_heads * AT_HD;
   if (at_tmap(&tq, c.Q, c.q_rows, cols, c.ldq, AT_BQ) != M5_OK) return M5_ERR_CUDA;
   if (at_tmap(&tk, c.K, c.k_rows, cols, c.ldk, AT_BK) != M5_OK) return M5_ERR_CUDA;
   if (at_tmap(&tv, c.V, c.k_rows, cols, c.ldv, AT_BK) != M5_OK) return M5_ERR_CUDA;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(flash_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) return M5_ERR_CUDA;
-    attr_set = true;
-  }
+  if (at_tmap(&tkl, split ? c.Klo : c.K, c.k_rows, cols, c.ldk, AT_BK) != M5_OK) return M5_ERR_CUDA;
+  if (at_tmap(&tvl, split ? c.Vlo : c.V, c.k_rows, cols, c.ldv, AT_BK) != M5_OK) return M5_ERR_CUDA;
+  // the opt-in shared-memory size is a per-device attribute: set it on every launch (cheap) instead of caching a flag
+  if (cudaFuncSetAttribute(flash_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<false>::SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(flash_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<true>::SMEM) != cudaSuccess)
+    return M5_ERR_CUDA;
   AttnTc5Params p;
-  p.q_start = c.q_start; p.q_len = c.q_len; p.k_start = c.k_start; p.k_len = c.k_len; p.O = c.O; p.ldo = c.ldo;
+  p.q_start = c.q_start; p.q_len = c.q_len; p.k_start = c.k_start; p.k_len = c.k_len; p.O = c.O; p.Olo = c.Olo; p.ldo = c.ldo;
   p.scale_log2 = c.scale * 1.4426950408889634f;
   dim3 grid((c.max_q + AT_BQ - 1) / AT_BQ, c.n_heads, c.n_seqs);
-  flash_tc5_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(tq, tk, tv, p);
+  if (split) flash_tc5_kernel<true><<<grid, AT_THREADS, AtCfg<true>::SMEM, stream>>>(tq, tk, tv, tkl, tvl, p);
+  else flash_tc5_kernel<false><<<grid, AT_THREADS, AtCfg<false>::SMEM, stream>>>(tq, tk, tv, tkl, tvl, p);
   return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
 }
 

@@ -56,18 +56,18 @@ cudaEvent_t prof_begin(m5_ctx* c) {
   cudaEventRecord(a, c->stream);
   return a;
 }
-void prof_end(m5_ctx* c, cudaEvent_t a, int kind, double flops, double bytes) {
+void prof_end(m5_ctx* c, cudaEvent_t a, int kind, double flops, double bytes, int64_t n) {
   if (!a) return;
   cudaEvent_t b = prof_get(c);
   cudaEventRecord(b, c->stream);
-  c->prof_pending.push_back({a, b, kind, flops, bytes});
+  c->prof_pending.push_back({a, b, kind, flops, bytes, n});
   if (c->prof_pending.size() >= 4096) { cudaStreamSynchronize(c->stream); prof_resolve(c); }
 }
 void prof_resolve(m5_ctx* c) {
   for (auto& r : c->prof_pending) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
-      c->prof_ms[r.kind] += ms; c->prof_flops[r.kind] += r.flops; c->prof_bytes[r.kind] += r.bytes; c->prof_n[r.kind] += 1;
+      c->prof_ms[r.kind] += ms; c->prof_flops[r.kind] += r.flops; c->prof_bytes[r.kind] += r.bytes; c->prof_n[r.kind] += r.n;
     }
     c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b);
   }
@@ -205,6 +205,22 @@ int m5_dbg_attn(m5_ctx* ctx, const void* Q, const void* K, const void* V, int32_
   c.q_len = q_len; c.k_start = k_start; c.k_len = k_len; c.causal = causal; c.q_rows = q_rows; c.k_rows = k_rows;
   int r = impl == 2 ? flash_attn_tc5(c, ctx->stream) : flash_attn(c, ctx->stream);
   if (r != M5_OK) return ctx->fail(r, "flash_attn failed");
+  ctx->launches += 1;
+  return M5_OK;
+}
+
+int m5_dbg_attn_split(m5_ctx* ctx, const void* Q, const void* K, const void* V, const void* Klo, const void* Vlo,
+                      int32_t ldq, int32_t ldk, int32_t ldv, void* O, void* Olo, int32_t ldo, int32_t n_heads,
+                      int32_t n_seqs, int32_t max_q, const int32_t* q_start, const int32_t* q_len, const int32_t* k_start,
+                      const int32_t* k_len, int32_t q_rows, int32_t k_rows) {
+  if (!ctx || !Klo || !Vlo || !Olo) return M5_ERR_ARG;
+  AttnCall c;
+  c.Q = (const __half*)Q; c.K = (const __half*)K; c.V = (const __half*)V; c.Klo = (const __half*)Klo; c.Vlo = (const __half*)Vlo;
+  c.ldq = ldq; c.ldk = ldk; c.ldv = ldv; c.O = (__half*)O; c.Olo = (__half*)Olo; c.ldo = ldo; c.n_heads = n_heads;
+  c.n_seqs = n_seqs; c.max_q = max_q; c.q_start = q_start; c.q_len = q_len; c.k_start = k_start; c.k_len = k_len;
+  c.q_rows = q_rows; c.k_rows = k_rows;
+  int r = flash_attn_tc5(c, ctx->stream);
+  if (r != M5_OK) return ctx->fail(r, "flash_attn_tc5 (split) failed");
   ctx->launches += 1;
   return M5_OK;
 }

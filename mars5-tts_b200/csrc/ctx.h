@@ -16,7 +16,7 @@ struct m5_ctx {
   int64_t launches = 0;
 
   // optional kernel-class profiling (bench.py roofline leg): event pairs resolved at the end of a public call
-  struct ProfRec { cudaEvent_t a, b; int kind; double flops, bytes; };
+  struct ProfRec { cudaEvent_t a, b; int kind; double flops, bytes; int64_t n; };
   bool prof_on = false;
   std::vector<ProfRec> prof_pending;
   std::vector<cudaEvent_t> prof_pool;
@@ -65,7 +65,7 @@ struct Arena {
 const m5_tensor* find_weight(m5_ctx* c, const std::string& name);
 // profiling helpers: bracket one launch with events when profiling is on
 cudaEvent_t prof_begin(m5_ctx* c);
-void prof_end(m5_ctx* c, cudaEvent_t a, int kind, double flops, double bytes);
+void prof_end(m5_ctx* c, cudaEvent_t a, int kind, double flops, double bytes, int64_t n = 1);
 void prof_resolve(m5_ctx* c);  // call after a stream synchronize
 template <typename T>
 inline const T* W(m5_ctx* c, const std::string& name) {

@@ -9,7 +9,7 @@
 namespace m5 {
 
 // epilogue kinds (compile-time)
-enum { E_F32 = 0, E_F32_ACC = 1, E_F16 = 2, E_SWIGLU = 3, E_GENERIC = 4 };
+enum { E_F32 = 0, E_F32_ACC = 1, E_F16 = 2, E_SWIGLU = 3, E_GENERIC = 4, E_F16_SPLIT = 5, E_SWIGLU_SPLIT = 6 };
 
 struct GemmEpi {
   const float* bias;      // [N] fp32 or null
@@ -62,6 +62,31 @@ __device__ __forceinline__ void epi_store4(const GemmEpi& epi, float (&v)[4], co
     const __half h0 = __float2half_rn(silu_f(v[0]) * v[1]), h1 = __float2half_rn(silu_f(v[2]) * v[3]);
     if (full4) *reinterpret_cast<uint32_t*>(o) = pack_h2(h0, h1);
     else if (col + 1 < N) o[0] = h0;
+  } else if constexpr (KIND == E_F16_SPLIT) {
+    // fp16 (hi, lo) pair of every value: hi = rn(v), lo = rn(v - hi); the mixed / precise NAR modes
+    __half* o = reinterpret_cast<__half*>(epi.out) + (size_t)row * epi.ldc + col;
+    __half* ol = reinterpret_cast<__half*>(epi.out_lo) + (size_t)row * epi.ldc + col;
+    __half h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { h[e] = __float2half_rn(v[e]); l[e] = __float2half_rn(v[e] - __half2float(h[e])); }
+    if (full4) {
+      *reinterpret_cast<uint2*>(o) = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
+      *reinterpret_cast<uint2*>(ol) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 3; ++e)
+        if (col + e < N) { o[e] = h[e]; ol[e] = l[e]; }
+    }
+  } else if constexpr (KIND == E_SWIGLU_SPLIT) {
+    __half* o = reinterpret_cast<__half*>(epi.out) + (size_t)row * epi.ldc + (col >> 1);
+    __half* ol = reinterpret_cast<__half*>(epi.out_lo) + (size_t)row * epi.ldc + (col >> 1);
+    const float g0 = silu_f(v[0]) * v[1], g1 = silu_f(v[2]) * v[3];
+    const __half h0 = __float2half_rn(g0), h1 = __float2half_rn(g1);
+    const __half l0 = __float2half_rn(g0 - __half2float(h0)), l1 = __float2half_rn(g1 - __half2float(h1));
+    if (full4) {
+      *reinterpret_cast<uint32_t*>(o) = pack_h2(h0, h1);
+      *reinterpret_cast<uint32_t*>(ol) = pack_h2(l0, l1);
+    } else if (col + 1 < N) { o[0] = h0; ol[0] = l0; }
   } else {  // E_GENERIC: activations, column scale, split (hi | lo) outputs -- cold paths (vocoder, timestep MLPs, precise mode)
     if (epi.act == M5_ACT_GELU) {
 #pragma unroll
@@ -141,6 +166,8 @@ static inline int gemm_epi_kind(const GemmCall& g) {
   if (plain && g.mode == M5_OUT_F32 && g.accumulate) return E_F32_ACC;
   if (plain && g.mode == M5_OUT_F16 && !g.colscale) return E_F16;
   if (plain && g.mode == M5_OUT_SWIGLU_F16 && !g.colscale) return E_SWIGLU;
+  if (plain && g.mode == M5_OUT_F16_SPLIT && !g.colscale) return E_F16_SPLIT;
+  if (plain && g.mode == M5_OUT_SWIGLU_F16_SPLIT && !g.colscale) return E_SWIGLU_SPLIT;
   return E_GENERIC;
 }
 

@@ -272,12 +272,15 @@ static int launch_kind(const GemmCall& g, cudaStream_t stream, int num_sms) {
 
 template <int BLOCK_N>
 static int launch_bn(const GemmCall& g, cudaStream_t stream, int num_sms) {
-  const bool plain = g.act == M5_ACT_NONE;
-  if (plain && g.mode == M5_OUT_F32 && !g.accumulate && !g.colscale) return launch_kind<BLOCK_N, E_F32>(g, stream, num_sms);
-  if (plain && g.mode == M5_OUT_F32 && g.accumulate) return launch_kind<BLOCK_N, E_F32_ACC>(g, stream, num_sms);
-  if (plain && g.mode == M5_OUT_F16 && !g.colscale) return launch_kind<BLOCK_N, E_F16>(g, stream, num_sms);
-  if (plain && g.mode == M5_OUT_SWIGLU_F16 && !g.colscale) return launch_kind<BLOCK_N, E_SWIGLU>(g, stream, num_sms);
-  return launch_kind<BLOCK_N, E_GENERIC>(g, stream, num_sms);
+  switch (gemm_epi_kind(g)) {
+    case E_F32: return launch_kind<BLOCK_N, E_F32>(g, stream, num_sms);
+    case E_F32_ACC: return launch_kind<BLOCK_N, E_F32_ACC>(g, stream, num_sms);
+    case E_F16: return launch_kind<BLOCK_N, E_F16>(g, stream, num_sms);
+    case E_SWIGLU: return launch_kind<BLOCK_N, E_SWIGLU>(g, stream, num_sms);
+    case E_F16_SPLIT: return launch_kind<BLOCK_N, E_F16_SPLIT>(g, stream, num_sms);
+    case E_SWIGLU_SPLIT: return launch_kind<BLOCK_N, E_SWIGLU_SPLIT>(g, stream, num_sms);
+    default: return launch_kind<BLOCK_N, E_GENERIC>(g, stream, num_sms);
+  }
 }
 
 int gemm_tc5(const GemmCall& g, cudaStream_t stream, int num_sms) {

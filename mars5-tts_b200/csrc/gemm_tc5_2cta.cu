@@ -302,6 +302,8 @@ int gemm_tc5_2cta(const GemmCall& g, cudaStream_t stream, int num_sms) {
     case E_F32_ACC: return launch_2cta<E_F32_ACC>(g, stream, num_sms);
     case E_F16: return launch_2cta<E_F16>(g, stream, num_sms);
     case E_SWIGLU: return launch_2cta<E_SWIGLU>(g, stream, num_sms);
+    case E_F16_SPLIT: return launch_2cta<E_F16_SPLIT>(g, stream, num_sms);
+    case E_SWIGLU_SPLIT: return launch_2cta<E_SWIGLU_SPLIT>(g, stream, num_sms);
     default: return launch_2cta<E_GENERIC>(g, stream, num_sms);
   }
 }

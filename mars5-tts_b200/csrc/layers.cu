@@ -87,15 +87,16 @@ static GemmCall lin(const __half* A, int rows, int K, bool split, const __half* 
 
 // shared FFN tail: x += W2 * swiglu(WV * LN(x)) + b2
 static int ffn_block(m5_ctx* ctx, float* x, int rows, int D, int ff, const float* nw, const float* nb, float eps,
-                     const __half* wv, const __half* w2, const float* b2, bool precise, const BlockScratch& s) {
-  M5_TRY(ln_to_f16(ctx, x, rows, D, nw, nb, eps, precise, s.h16));
-  GemmCall g1 = lin(s.h16, rows, D, precise, wv, 2 * ff, nullptr);
+                     const __half* wv, const __half* w2, const float* b2, int mode, const BlockScratch& s) {
+  const bool split = mode != M5_NUM_FAST;
+  M5_TRY(ln_to_f16(ctx, x, rows, D, nw, nb, eps, split, s.h16));
+  GemmCall g1 = lin(s.h16, rows, D, split, wv, 2 * ff, nullptr);
   g1.out = s.g16;
-  g1.out_lo = precise ? s.g16 + ff : nullptr;
-  g1.ldc = precise ? 2 * ff : ff;
-  g1.mode = precise ? M5_OUT_SWIGLU_F16_SPLIT : M5_OUT_SWIGLU_F16;
+  g1.out_lo = split ? s.g16 + ff : nullptr;
+  g1.ldc = split ? 2 * ff : ff;
+  g1.mode = split ? M5_OUT_SWIGLU_F16_SPLIT : M5_OUT_SWIGLU_F16;
   M5_TRY(run_gemm(ctx, g1));
-  GemmCall g2 = lin(s.g16, rows, ff, precise, w2, D, b2);
+  GemmCall g2 = lin(s.g16, rows, ff, split, w2, D, b2);
   g2.out = x; g2.ldc = D; g2.mode = M5_OUT_F32; g2.accumulate = 1;
   M5_TRY(run_gemm(ctx, g2));
   return M5_OK;
@@ -103,58 +104,70 @@ static int ffn_block(m5_ctx* ctx, float* x, int rows, int D, int ff, const float
 
 // x += out_proj(softmax(q k^T / 8) v): shared by self- and cross-attention.  Queries come from h16 (already normalised),
 // keys/values either from the same projection (kv_src == nullptr) or from the encoder memory.
-static int attn_block(m5_ctx* ctx, float* x, const SeqSet& seqs, int D, int H, bool precise, const BlockScratch& s,
+static int attn_block(m5_ctx* ctx, float* x, const SeqSet& seqs, int D, int H, int mode, const BlockScratch& s,
                       const __half* in_w, const float* in_b, const __half* out_w, const float* out_b,
                       const __half* mem16, const SeqSet* mem_seqs, const __half* kv_w, const float* kv_b) {
   const int rows = seqs.rows;
   const bool cross = mem16 != nullptr;
+  const bool split = mode != M5_NUM_FAST;
+  // mixed: sequences long enough for the tcgen05 kernel keep Q (and P) single fp16 and carry K, V, O as pairs; shorter
+  // ones (text encoder, tiny inputs) run the fully split mma.sync kernel
+  const bool tc5_split = mode == M5_NUM_MIXED && seqs.max_len >= 256;
+  const bool q_pair = split && !tc5_split;   // does the attention kernel consume low halves of Q?
   const int qn = cross ? D : 3 * D;  // width of the projection of h16
-  GemmCall gq = lin(s.h16, rows, D, precise, in_w, qn, in_b);
-  gq.out = s.qkv16; gq.ldc = qn; gq.mode = precise ? M5_OUT_F16_SPLIT : M5_OUT_F16; gq.out_lo = precise ? s.qkv16_lo : nullptr;
+  GemmCall gq = lin(s.h16, rows, D, split && !(cross && tc5_split), in_w, qn, in_b);
+  if (cross && tc5_split) gq.lda = 2 * D;  // hi halves only: the rounding of a cross-attention query is 2e-5 rms on the logits
+  gq.out = s.qkv16; gq.ldc = qn;
+  const bool q_out_pair = cross ? q_pair : split;   // the fused QKV projection always needs the K / V low halves
+  gq.mode = q_out_pair ? M5_OUT_F16_SPLIT : M5_OUT_F16; gq.out_lo = q_out_pair ? s.qkv16_lo : nullptr;
   M5_TRY(run_gemm(ctx, gq));
   AttnCall a;
-  a.Q = s.qkv16; a.ldq = qn; a.Qlo = precise ? s.qkv16_lo : nullptr;
+  a.Q = s.qkv16; a.ldq = qn; a.Qlo = q_pair ? s.qkv16_lo : nullptr;
   if (cross) {
-    GemmCall gkv = lin(mem16, mem_seqs->rows, D, precise, kv_w, 2 * D, kv_b);
-    gkv.out = s.kv16; gkv.ldc = 2 * D; gkv.mode = precise ? M5_OUT_F16_SPLIT : M5_OUT_F16; gkv.out_lo = precise ? s.kv16_lo : nullptr;
+    GemmCall gkv = lin(mem16, mem_seqs->rows, D, split, kv_w, 2 * D, kv_b);
+    gkv.out = s.kv16; gkv.ldc = 2 * D; gkv.mode = split ? M5_OUT_F16_SPLIT : M5_OUT_F16; gkv.out_lo = split ? s.kv16_lo : nullptr;
     M5_TRY(run_gemm(ctx, gkv));
     a.K = s.kv16; a.V = s.kv16 + D; a.ldk = a.ldv = 2 * D;
-    if (precise) { a.Klo = s.kv16_lo; a.Vlo = s.kv16_lo + D; }
+    if (split) { a.Klo = s.kv16_lo; a.Vlo = s.kv16_lo + D; }
     a.k_start = mem_seqs->start; a.k_len = mem_seqs->len; a.k_rows = mem_seqs->rows;
     a.flops_hint = 256.0 * H * seqs.cross_pairs;
   } else {
     a.K = s.qkv16 + D; a.V = s.qkv16 + 2 * D; a.ldk = a.ldv = 3 * D;
-    if (precise) { a.Klo = s.qkv16_lo + D; a.Vlo = s.qkv16_lo + 2 * D; }
+    if (split) { a.Klo = s.qkv16_lo + D; a.Vlo = s.qkv16_lo + 2 * D; }
     a.k_start = seqs.start; a.k_len = seqs.klen ? seqs.klen : seqs.len; a.k_rows = rows;
     a.flops_hint = 256.0 * H * seqs.self_pairs;
   }
-  a.O = s.att16; a.ldo = precise ? 2 * D : D; a.Olo = precise ? s.att16 + D : nullptr;
+  if (tc5_split) a.flops_hint *= 2.0;   // S and PV each run two UMMA passes (hi and lo tiles)
+  a.O = s.att16; a.ldo = split ? 2 * D : D; a.Olo = split ? s.att16 + D : nullptr;
   a.n_heads = H; a.n_seqs = seqs.n; a.max_q = seqs.max_len; a.q_start = seqs.start; a.q_len = seqs.len; a.q_rows = rows;
-  if (precise) a.impl = 1;  // the split-precision path lives in the mma.sync kernel
+  if (q_pair) a.impl = 1;        // the fully split path lives in the mma.sync kernel
+  else if (tc5_split) a.impl = 2;
   M5_TRY(run_attn(ctx, a));
-  GemmCall go = lin(s.att16, rows, D, precise, out_w, D, out_b);
+  GemmCall go = lin(s.att16, rows, D, split, out_w, D, out_b);
   go.out = x; go.ldc = D; go.mode = M5_OUT_F32; go.accumulate = 1;
   return run_gemm(ctx, go);
 }
 
 int encoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const EncLayerW& w, int D, int H, int ff, float eps,
-                  bool precise, const BlockScratch& s) {
+                  int mode, const BlockScratch& s) {
   const int rows = seqs.rows;
+  const bool split = mode != M5_NUM_FAST;
   // x = x + out_proj(MHA(LN1(x)))
-  M5_TRY(ln_to_f16(ctx, x, rows, D, w.n1w, w.n1b, eps, precise, s.h16));
-  M5_TRY(attn_block(ctx, x, seqs, D, H, precise, s, w.in_w, w.in_b, w.out_w, w.out_b, nullptr, nullptr, nullptr, nullptr));
+  M5_TRY(ln_to_f16(ctx, x, rows, D, w.n1w, w.n1b, eps, split, s.h16));
+  M5_TRY(attn_block(ctx, x, seqs, D, H, mode, s, w.in_w, w.in_b, w.out_w, w.out_b, nullptr, nullptr, nullptr, nullptr));
   // x = x + linear2(swiglu(LN2(x)))
-  return ffn_block(ctx, x, rows, D, ff, w.n2w, w.n2b, eps, w.wv, w.w2, w.b2, precise, s);
+  return ffn_block(ctx, x, rows, D, ff, w.n2w, w.n2b, eps, w.wv, w.w2, w.b2, mode, s);
 }
 
 int decoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const __half* mem16, const SeqSet& mem_seqs,
-                  const DecLayerW& w, int D, int H, int ff, float eps, bool precise, const BlockScratch& s) {
+                  const DecLayerW& w, int D, int H, int ff, float eps, int mode, const BlockScratch& s) {
   const int rows = seqs.rows;
-  M5_TRY(ln_to_f16(ctx, x, rows, D, w.n1w, w.n1b, eps, precise, s.h16));
-  M5_TRY(attn_block(ctx, x, seqs, D, H, precise, s, w.sa_in_w, w.sa_in_b, w.sa_out_w, w.sa_out_b, nullptr, nullptr, nullptr, nullptr));
-  M5_TRY(ln_to_f16(ctx, x, rows, D, w.n2w, w.n2b, eps, precise, s.h16));
-  M5_TRY(attn_block(ctx, x, seqs, D, H, precise, s, w.ca_q_w, w.ca_q_b, w.ca_out_w, w.ca_out_b, mem16, &mem_seqs, w.ca_kv_w, w.ca_kv_b));
-  return ffn_block(ctx, x, rows, D, ff, w.n3w, w.n3b, eps, w.wv, w.w2, w.b2, precise, s);
+  const bool split = mode != M5_NUM_FAST;
+  M5_TRY(ln_to_f16(ctx, x, rows, D, w.n1w, w.n1b, eps, split, s.h16));
+  M5_TRY(attn_block(ctx, x, seqs, D, H, mode, s, w.sa_in_w, w.sa_in_b, w.sa_out_w, w.sa_out_b, nullptr, nullptr, nullptr, nullptr));
+  M5_TRY(ln_to_f16(ctx, x, rows, D, w.n2w, w.n2b, eps, split, s.h16));
+  M5_TRY(attn_block(ctx, x, seqs, D, H, mode, s, w.ca_q_w, w.ca_q_b, w.ca_out_w, w.ca_out_b, mem16, &mem_seqs, w.ca_kv_w, w.ca_kv_b));
+  return ffn_block(ctx, x, rows, D, ff, w.n3w, w.n3b, eps, w.wv, w.w2, w.b2, mode, s);
 }
 
 }  // namespace m5

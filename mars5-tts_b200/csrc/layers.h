@@ -52,12 +52,19 @@ struct BlockScratch {
 size_t block_scratch_bytes(int rows, int mem_rows, int D, int ff);
 void block_scratch_carve(Arena& a, BlockScratch& s, int rows, int mem_rows, int D, int ff);
 
+// NAR numerics (m5_nar_cfg.precise):
+//   M5_NUM_FAST    every GEMM / attention operand is one fp16 value (fp32 accumulate)
+//   M5_NUM_PRECISE every activation operand is an fp16 (hi, lo) pair; attention in the 3-term mma.sync kernel
+//   M5_NUM_MIXED   GEMM activations, keys and values are (hi, lo) pairs, queries and probabilities single fp16; attention on
+//                  tcgen05 (split-KV kernel) -- the cheapest setting that holds 1e-3 max-abs on the logits
+enum { M5_NUM_FAST = 0, M5_NUM_PRECISE = 1, M5_NUM_MIXED = 2 };
+
 // x (fp32 [rows, D]) is updated in place.
 int encoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const EncLayerW& w, int D, int H, int ff, float eps,
-                  bool precise, const BlockScratch& s);
+                  int mode, const BlockScratch& s);
 // mem16: encoder output after its final LayerNorm as fp16 [mem rows, D*(precise?2:1)]
 int decoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const __half* mem16, const SeqSet& mem_seqs,
-                  const DecLayerW& w, int D, int H, int ff, float eps, bool precise, const BlockScratch& s);
+                  const DecLayerW& w, int D, int H, int ff, float eps, int mode, const BlockScratch& s);
 
 // convenience wrappers that count launches
 int run_gemm(m5_ctx* ctx, const GemmCall& g);

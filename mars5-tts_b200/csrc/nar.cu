@@ -227,7 +227,7 @@ static int nar_speaker(m5_ctx* ctx, const NarWeights& w, const NarPlan& p, const
   if (chunked_embed(e, ctx->stream) != M5_OK) return ctx->fail(M5_ERR_CUDA, "chunked_embed(spk) failed");
   ctx->launches++;
   for (int l = 0; l < c.nar_spk_layers; ++l)
-    M5_TRY(encoder_layer(ctx, nb.spk_x, p.spk, w.spk[l], c.nar_dim, c.nar_heads, c.nar_ff, c.ln_eps, true, nb.bs));
+    M5_TRY(encoder_layer(ctx, nb.spk_x, p.spk, w.spk[l], c.nar_dim, c.nar_heads, c.nar_ff, c.ln_eps, M5_NUM_PRECISE, nb.bs));
   NormCall n;
   n.x = nb.spk_x; n.M = p.B + 1; n.D = c.nar_dim; n.ldx = c.nar_dim; n.gamma = w.spk_nw; n.beta = w.spk_nb;
   n.eps = c.ln_eps; n.out_f32 = nb.spk_vec; n.ldo = c.nar_dim; n.row_map = p.spk_first;
@@ -258,17 +258,18 @@ static int nar_timestep_tables(m5_ctx* ctx, const NarWeights& w, int T, NarBuffe
 
 // One model evaluation at timestep t for every sequence of the plan; leaves the logits of the rows in p.lg_* in
 // nb.logits (codebook q -> logits for that head only; caller loops over q).
-static int nar_trunk(m5_ctx* ctx, const NarWeights& w, const NarPlan& p, const int* x_dev, int t, bool precise,
+static int nar_trunk(m5_ctx* ctx, const NarWeights& w, const NarPlan& p, const int* x_dev, int t, int mode,
                      NarBuffers& nb) {
   const m5_model_cfg& c = ctx->cfg;
   const int D = c.nar_dim;
+  const bool precise = mode != M5_NUM_FAST;   // are GEMM activations carried as (hi, lo) pairs?
   TokEmbedCall te;
   te.tok = p.enc_tok; te.pos = p.enc_pos; te.table = w.text_embed; te.vec_rows = nb.spk_vec; te.pe = w.pe;
   te.alpha = w.alpha_cond; te.add_vec = nb.t_enc + (size_t)t * D; te.n_rows = p.enc.rows; te.D = D; te.out = nb.xe;
   if (token_embed(te, ctx->stream) != M5_OK) return ctx->fail(M5_ERR_CUDA, "token_embed failed");
   ctx->launches++;
   for (int l = 0; l < c.nar_enc_layers; ++l)
-    M5_TRY(encoder_layer(ctx, nb.xe, p.enc, w.enc[l], D, c.nar_heads, c.nar_ff, c.ln_eps, precise, nb.bs));
+    M5_TRY(encoder_layer(ctx, nb.xe, p.enc, w.enc[l], D, c.nar_heads, c.nar_ff, c.ln_eps, mode, nb.bs));
   NormCall en;
   en.x = nb.xe; en.M = p.enc.rows; en.D = D; en.ldx = D; en.gamma = w.enc_nw; en.beta = w.enc_nb; en.eps = c.ln_eps;
   en.out = nb.mem16; en.out_lo = precise ? nb.mem16 + D : nullptr; en.ldo = precise ? 2 * D : D;
@@ -280,14 +281,15 @@ static int nar_trunk(m5_ctx* ctx, const NarWeights& w, const NarPlan& p, const i
   if (chunked_embed(de, ctx->stream) != M5_OK) return ctx->fail(M5_ERR_CUDA, "chunked_embed(dec) failed");
   ctx->launches++;
   for (int l = 0; l < c.nar_dec_layers; ++l)
-    M5_TRY(decoder_layer(ctx, nb.xd, p.dec, nb.mem16, p.enc, w.dec[l], D, c.nar_heads, c.nar_ff, c.ln_eps, precise, nb.bs));
+    M5_TRY(decoder_layer(ctx, nb.xd, p.dec, nb.mem16, p.enc, w.dec[l], D, c.nar_heads, c.nar_ff, c.ln_eps, mode, nb.bs));
   NormCall dn;
   dn.x = nb.xd; dn.M = p.npass * p.n_lg; dn.D = D; dn.ldx = D; dn.gamma = w.dec_nw; dn.beta = w.dec_nb; dn.eps = c.ln_eps;
   dn.out_f32 = nb.dn; dn.ldo = D; dn.row_map = p.lg_decrow;
   return run_norm(ctx, dn);
 }
 
-static int nar_head(m5_ctx* ctx, const NarWeights& w, const NarPlan& p, int q, bool precise, NarBuffers& nb) {
+static int nar_head(m5_ctx* ctx, const NarWeights& w, const NarPlan& p, int q, int mode, NarBuffers& nb) {
+  const bool precise = mode != M5_NUM_FAST;
   const m5_model_cfg& c = ctx->cfg;
   const int D = c.nar_dim, R = p.npass * p.n_lg;
   NormCall hn;
@@ -385,7 +387,7 @@ extern "C" {
 int m5_nar_forward(m5_ctx* ctx, int32_t B, const int32_t* c_text, const int32_t* c_text_len, const int32_t* c_codes,
                    const int32_t* c_codes_len, const int32_t* x, const int32_t* x_len, int32_t t, int32_t drop_cond,
                    int32_t precise, int32_t mem, float* logits_out) {
-  if (!ctx || B <= 0) return M5_ERR_ARG;
+  if (!ctx || B <= 0 || precise < 0 || precise > 2) return M5_ERR_ARG;
   ctx->last_error.clear();
   cudaSetDevice(ctx->device);
   NarWeights w;
@@ -415,9 +417,9 @@ int m5_nar_forward(m5_ctx* ctx, int32_t B, const int32_t* c_text, const int32_t*
   M5_TRY(carve(ctx, ar, p, T, nb));
   M5_TRY(nar_speaker(ctx, w, p, d_codes, nb));
   M5_TRY(nar_timestep_tables(ctx, w, T, nb));
-  M5_TRY(nar_trunk(ctx, w, p, d_x, t, precise != 0, nb));
+  M5_TRY(nar_trunk(ctx, w, p, d_x, t, precise, nb));
   for (int q = 0; q < c.n_quant; ++q) {
-    M5_TRY(nar_head(ctx, w, p, q, precise != 0, nb));
+    M5_TRY(nar_head(ctx, w, p, q, precise, nb));
     scatter_logits_kernel<<<148 * 4, 256, 0, ctx->stream>>>(nb.logits, nb.ldl, d_out, p.n_lg, c.n_quant, c.n_classes, q);
     ctx->launches++;
   }
@@ -432,13 +434,15 @@ int m5_nar_infer(m5_ctx* ctx, int32_t B, const int32_t* c_text, const int32_t* c
                  int32_t mem, const int32_t* x_init, const float* noise, uint64_t seed, const int64_t* utt_ids,
                  int32_t* out_codes) {
   if (!ctx || !cfg || B <= 0) return M5_ERR_ARG;
+  if (cfg->precise < 0 || cfg->precise > 2) return ctx->fail(M5_ERR_ARG, "m5_nar_cfg.precise must be 0 (fast), 1 (precise) or 2 (mixed)");
   ctx->last_error.clear();
   cudaSetDevice(ctx->device);
   NarWeights w;
   M5_TRY(load_nar(ctx, w));
   const m5_model_cfg& c = ctx->cfg;
   const int T = cfg->T, Q = c.n_quant, K = c.n_classes;
-  const bool deep = cfg->deep_clone != 0, precise = cfg->precise != 0;
+  const bool deep = cfg->deep_clone != 0;
+  const int precise = cfg->precise;   // M5_NUM_*
   const bool cfg_on = cfg->guidance_w != 1.0f;  // diffuser.py:361
   const int npass = cfg_on ? 2 : 1;
   size_t n_text = 0, n_codes = 0, n_x = 0, Rx = 0;

@@ -4,6 +4,7 @@ tiny model in test_pipeline_gpu.py; here the kernels that carry the step are run
 compared with plain PyTorch fp32 evaluations of the same op -- whole-output for the GEMMs, per-sequence for attention."""
 import ctypes as C
 
+import numpy as np
 import pytest
 import torch
 
@@ -124,3 +125,142 @@ def test_decode_attention_full_batch(m5lib, bare_ctx):
                         vc[b, :lens[b]].float().view(-1, H, 64)).reshape(-1)
         err = (out[b].float() - ref).abs().max().item()
         assert err < 3e-3, (b, lens[b], err)
+
+
+def test_flash_attention_split_kv(m5lib, bare_ctx):
+    """"mixed" numerics: keys and values as fp16 (hi, lo) pairs, queries / probabilities single fp16, output a pair.
+    Against an fp32 softmax(Q K^T / 8) V of the UNROUNDED keys / values the pair kernel must be several times closer
+    than the plain fp16 kernel, at the NAR decoder length and at the cross-attention length."""
+    H, D = 16, 1024
+    q_lens = [2399, 700, 2399]
+    for k_lens, seed in ((q_lens, 31), ([137, 137, 5], 32)):
+        g = torch.Generator(device=DEV).manual_seed(seed)
+        nq, nk = sum(q_lens), sum(k_lens)
+        Q = (torch.randn(nq, D, device=DEV, generator=g)).half()
+        K32, V32 = torch.randn(nk, D, device=DEV, generator=g), torch.randn(nk, D, device=DEV, generator=g)
+        Kh, Vh = K32.half(), V32.half()
+        Kl, Vl = (K32 - Kh.float()).half(), (V32 - Vh.float()).half()
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=DEV)
+        cs = lambda v: [sum(v[:i]) for i in range(len(v))]
+        qs, ql, ks, kl = i32(cs(q_lens)), i32(q_lens), i32(cs(k_lens)), i32(k_lens)
+        O, Ol = torch.zeros(nq, D, device=DEV, dtype=torch.float16), torch.zeros(nq, D, device=DEV, dtype=torch.float16)
+        rc = m5lib.m5_dbg_attn_split(bare_ctx, ptr(Q), ptr(Kh), ptr(Vh), ptr(Kl), ptr(Vl), D, D, D, ptr(O), ptr(Ol), D, H, len(q_lens),
+                                     max(q_lens), ptr(qs), ptr(ql), ptr(ks), ptr(kl), nq, nk)
+        capi.check(bare_ctx, rc, "attn_split")
+        Op = torch.zeros(nq, D, device=DEV, dtype=torch.float16)
+        rc = m5lib.m5_dbg_attn(bare_ctx, ptr(Q), ptr(Kh), ptr(Vh), D, D, D, ptr(Op), D, H, len(q_lens), max(q_lens), ptr(qs), ptr(ql),
+                               ptr(ks), ptr(kl), 0, 2, nq, nk)
+        capi.check(bare_ctx, rc, "attn")
+        _sync(m5lib, bare_ctx)
+        e_split = e_plain = 0.0
+        for i, (qn, kn) in enumerate(zip(q_lens, k_lens)):
+            q0, k0 = cs(q_lens)[i], cs(k_lens)[i]
+            ref = _attn_ref(Q[q0:q0 + qn].float().view(qn, H, 64), K32[k0:k0 + kn].view(kn, H, 64), V32[k0:k0 + kn].view(kn, H, 64)).reshape(qn, D)
+            e_split = max(e_split, ((O[q0:q0 + qn].float() + Ol[q0:q0 + qn].float()) - ref).abs().max().item())
+            e_plain = max(e_plain, (Op[q0:q0 + qn].float() - ref).abs().max().item())
+        print(f"split-KV attention: max-abs {e_split:.2e} (plain fp16 kernel {e_plain:.2e}), keys {k_lens}")
+        assert e_split < 6e-4 and e_split < 0.5 * e_plain, (k_lens, e_split, e_plain)
+
+
+# ------------------------------------------------------------------------------------------------ full-size pipelines
+@pytest.fixture(scope="module")
+def full_engine():
+    """FULL model dims (AR 1536 x 26, NAR 1024 x 8/16/3, V = 8000), seeded synthetic reference-format checkpoints."""
+    from mars5_tts_b200 import synth, weights
+    from mars5_tts_b200.engine import Engine
+    torch.set_grad_enabled(False)
+    size = synth.FULL
+    ar_sd, nar_sd, voc_sd = synth.make_ar_state(size), synth.make_nar_state(size), synth.make_vocos_state(size)
+    eng = Engine(ar_sd, nar_sd, voc_sd, size["n_text"], device=0, max_pos=4096)
+    cfg = weights.dims_from_state(ar_sd, nar_sd, voc_sd, size["n_text"])
+    yield size, ar_sd, nar_sd, eng, cfg
+    eng.close()
+
+
+def test_nar_forward_full_dims_absolute_tolerance(full_engine):
+    """BASELINE north_star: <= 1e-3 MAX-ABS on the NAR logits against the reference's fp32 arithmetic, at the full model
+    dims and a BASELINE configs[1]-sized sequence (S = 1650 decoder rows, 86 text tokens, 450 reference frames).  `mixed`
+    (the mode bench.py and Mars5TTS run) and `precise` must hold the absolute bound; `fast` is reported and held to the
+    relative bound only (it does NOT meet the north_star tolerance: fp16 activations have a 2^-11 relative error floor)."""
+    from mars5_tts_b200 import capi as cp
+    from oracle import nar_oracle
+    size, _, nar_sd, eng, cfg = full_engine
+    g = torch.Generator().manual_seed(17)
+    S, Tc, Pf, t = 1650, 86, 450, 100
+    text = torch.randint(0, size["n_text"], (Tc,), generator=g)
+    codes = torch.randint(0, 1024, (Pf, 8), generator=g)
+    x = torch.randint(0, 1025, (S, 8), generator=g)
+    torch.set_num_threads(min(32, torch.get_num_threads()))
+    ref = nar_oracle.nar_forward(nar_sd, cfg, text, codes, x, t).numpy()
+    scale = float(np.abs(ref).max())
+    errs = {}
+    for name, mode in (("fast", cp.NUM_FAST), ("mixed", cp.NUM_MIXED), ("precise", cp.NUM_PRECISE)):
+        got = eng.nar_forward([text.numpy()], [codes.numpy()], [x.numpy()], t, precise=mode)[0]
+        errs[name] = float(np.abs(got - ref).max())
+    print(f"NAR logits at full dims (S={S}): max|logit| {scale:.2f}; max-abs error " + ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
+    assert errs["mixed"] < 1e-3, errs
+    assert errs["precise"] < 1e-3, errs
+    assert errs["fast"] < 1e-3 * max(1.0, scale), errs
+
+
+def test_nar_forward_full_dims_uncond_and_batch(full_engine):
+    """Unconditional pass (speaker encoder sees only the identity token) and a second, shorter utterance in the same
+    packed batch: rows of a batch equal single-utterance runs, mixed numerics, absolute bound."""
+    from mars5_tts_b200 import capi as cp
+    from oracle import nar_oracle
+    size, _, nar_sd, eng, cfg = full_engine
+    g = torch.Generator().manual_seed(18)
+    texts = [torch.randint(0, size["n_text"], (n,), generator=g) for n in (40, 12)]
+    codes = [torch.randint(0, 1024, (n, 8), generator=g) for n in (300, 450)]
+    xs = [torch.randint(0, 1025, (n, 8), generator=g) for n in (700, 300)]
+    got = eng.nar_forward([a.numpy() for a in texts], [c.numpy() for c in codes], [x.numpy() for x in xs], 7, drop_cond=True,
+                          precise=cp.NUM_MIXED)
+    for i in range(2):
+        ref = nar_oracle.nar_forward(nar_sd, cfg, texts[i], codes[i], xs[i], 7, drop_cond=True).numpy()
+        err = float(np.abs(got[i] - ref).max())
+        print(f"uncond utterance {i}: max-abs {err:.2e}")
+        assert err < 1e-3, (i, err)
+
+
+def test_ar_forward_full_dims(full_engine):
+    """CodecLM.forward at the full dims over a BASELINE-sized prompt (135 text + 450 speech tokens, 450-frame speaker
+    reference) against the fp32 oracle.  The AR engine mirrors the reference's GPU arithmetic (fp16 autocast,
+    inference.py:263 / SURVEY B.1: fp16 GEMM operands and KV cache, fp32 residual stream), which the reference itself
+    only holds to fp16 accuracy against its own CPU fp32 path -- the max-abs error is reported and bounded relative to
+    the logit scale; the sampled tokens are pinned bit-exact against the reference in test_pipeline_gpu.py."""
+    from oracle import ar_oracle
+    size, ar_sd, _, eng, cfg = full_engine
+    g = torch.Generator().manual_seed(19)
+    P, Pf = 586, 450
+    prompt = torch.cat([torch.randint(0, size["n_text"], (136,), generator=g),
+                        torch.randint(size["n_text"], size["n_text"] + 1024, (P - 136,), generator=g)])
+    spk = torch.randint(0, 1024, (Pf, 8), generator=g)
+    got = eng.ar_forward([prompt.tolist()], [spk.numpy()])[0]
+    ref = ar_oracle.codeclm_forward(ar_sd, cfg, prompt, spk).numpy()
+    err, scale = float(np.abs(got - ref).max()), float(np.abs(ref).max())
+    print(f"AR logits at full dims (P={P}): max|logit| {scale:.2f}; max-abs error {err:.2e} (rel {err / scale:.2e})")
+    assert err < 2e-3 * max(1.0, scale), (err, scale)
+    assert (got.argmax(-1) == ref.argmax(-1)).mean() > 0.995
+
+
+def test_nar_infer_full_dims_code_agreement(full_engine):
+    """Whole reverse loop at the full dims (T = 20, CFG, in-kernel Philox noise keyed by utterance id): the codes of the
+    `mixed` and `fast` modes against the `precise` mode (which is pinned bit-exact against the reference's own outputs on
+    the tiny model, test_pipeline_gpu.py).  Sampling feeds back through x_t, so a single flipped Gumbel arg-max early on
+    decorrelates later steps -- the mismatch RATE is the parity figure."""
+    from mars5_tts_b200 import capi as cp
+    from mars5_tts_b200.engine import InferenceConfig
+    size, _, _, eng, _ = full_engine
+    g = torch.Generator().manual_seed(23)
+    B, Tc, Pf, N = 2, 60, 200, 400
+    texts = [torch.randint(0, size["n_text"], (Tc,), generator=g).numpy().astype(np.int32) for _ in range(B)]
+    codes = [torch.randint(0, 1024, (Pf, 8), generator=g).numpy().astype(np.int32) for _ in range(B)]
+    l0 = [torch.randint(0, 1024, (N,), generator=g).numpy().astype(np.int32) for _ in range(B)]
+    out = {}
+    for name, mode in (("precise", cp.NUM_PRECISE), ("mixed", cp.NUM_MIXED), ("fast", cp.NUM_FAST)):
+        ncfg = eng.make_nar_cfg(InferenceConfig(), T=20, precise=mode)
+        out[name] = np.stack(eng.nar_infer(texts, codes, l0, ncfg, seed=5, utt_ids=[100, 101]))
+    mm = {k: float((out[k] != out["precise"]).mean()) for k in ("mixed", "fast")}
+    print(f"NAR codes after T=20 at full dims vs precise: mixed {mm['mixed']:.4%} differ, fast {mm['fast']:.4%} differ")
+    assert mm["mixed"] <= 0.02, mm
+    assert mm["mixed"] <= mm["fast"] + 1e-9 or mm["fast"] < 0.02, mm
