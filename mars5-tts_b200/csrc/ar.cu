@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "ar_decode.h"
 #include "layers.h"
 #include "ptx.cuh"
 #include "sampler.h"
@@ -375,7 +376,8 @@ int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int3
   const size_t dump_bytes = (logits_dump && mem == M5_MEM_HOST) ? (size_t)B * dump_steps * V * 4 : 0;
   size_t bytes = block_scratch_bytes(big, 0, D, ffmax) + (size_t)spk_rows * D * 4 + (size_t)B * D * 4 + (size_t)rows * D * 4 + cache_bytes +
                  noise_bytes + dump_bytes + (size_t)B * (max_len + 64) * 4 + (size_t)B * (3 * D + V + 4 * D + F) * 4 +
-                 decode_attn_scratch_bytes(B, c.ar_heads, n_split) + (n_ids + n_codes * Q) * 4 + (size_t)(rows + spk_rows) * 64 + (size_t(32) << 20);
+                 decode_attn_scratch_bytes(B, c.ar_heads, n_split) + (n_ids + n_codes * Q) * 4 + (size_t)(rows + spk_rows) * 64 + (size_t(32) << 20) +
+                 ar_decode_attn_floats(B, c.ar_heads, ar_decode_splits_for(Wc)) * 4 + (size_t)(4 * ctx->num_sms + 64) * 32 * 128 * 4;
   M5_TRY(ar.reserve(bytes));
   ArPlan p;
   M5_TRY(ar_build_plan(ctx, ar, p, B, prompt_len, spk_len));
@@ -400,6 +402,29 @@ int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int3
   st.g16 = ar.get<__half>((size_t)B * F);
   st.attn_scratch = ar.get<float>(decode_attn_scratch_bytes(B, c.ar_heads, n_split) / 4);
   st.n_split = n_split;
+  // fused persistent decode kernel (ar_decode.cu); M5_AR_DECODE_LEGACY=1 keeps the per-kernel graph of round 1 for A/B runs
+  static const bool legacy_decode = getenv("M5_AR_DECODE_LEGACY") != nullptr;
+  ArDecodeParams dp;
+  dp.B = B; dp.n_layers = L; dp.D = D; dp.F = F; dp.H = c.ar_heads; dp.V = V; dp.Wc = Wc; dp.eps = c.ar_norm_eps;
+  dp.final_norm = w.norm; dp.embed = w.embed; dp.inv_freq = w.inv_freq;
+  dp.ids = st.ids; dp.ids_stride = max_len; dp.tok_len = st.tok_len; dp.kv_len = st.kv_len; dp.done = st.done;
+  dp.x = st.x; dp.qkv = st.qkv32; dp.g16 = st.g16; dp.logits = st.logits; dp.kc = kc; dp.vc = vc;
+  M5_TRY(ar_decode_plan(dp, ctx->num_sms));
+  dp.g_out.W = w.output;
+  dp.n_split = ar_decode_splits_for(Wc);
+  {
+    std::vector<ArLayerDev> hl(L);
+    for (int l = 0; l < L; ++l) hl[l] = {w.layers[l].attn_norm, w.layers[l].ffn_norm, w.layers[l].wqkv, w.layers[l].wo, w.layers[l].w13, w.layers[l].w2};
+    dp.layers = upload(ctx, ar, hl);
+    dp.ssq = ar.get<float>((size_t)dp.ssq_tiles * 32);
+    dp.attn_part = ar.get<float>(ar_decode_attn_floats(B, c.ar_heads, dp.n_split));
+    dp.scratch = ar.get<float>(ar_decode_scratch_floats(dp));
+    dp.counters = ar.get<int>(ar_decode_max_tiles(dp) + 1);
+    dp.gbar = reinterpret_cast<unsigned*>(ar.get<int>(4));
+    if (!dp.layers || !dp.ssq || !dp.attn_part || !dp.scratch || !dp.counters || !dp.gbar)
+      return ctx->fail(M5_ERR_NOMEM, "arena too small (fused decode buffers)");
+    cudaMemsetAsync(dp.counters, 0, (ar_decode_max_tiles(dp) + 1) * sizeof(int), ctx->stream);
+  }
   const float* d_noise = noise;
   if (noise && mem == M5_MEM_HOST) {
     float* dn = ar.get<float>((size_t)B * noise_steps * V);
@@ -445,7 +470,17 @@ int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int3
     M5_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     static const bool no_pdl = getenv("M5_DISABLE_PDL") != nullptr;
     g_use_pdl = !no_pdl;  // kernels of the step overlap their prologues (weight prefetch) with their predecessor's tail
-    int rc = ar_decode_step(ctx, w, B, st, kc, vc, Wc, sc);
+    int rc;
+    if (legacy_decode) {
+      rc = ar_decode_step(ctx, w, B, st, kc, vc, Wc, sc);
+    } else {
+      g_use_pdl = false;
+      rc = ar_decode_launch(dp, ctx->num_sms, ctx->stream);
+      if (rc != M5_OK) ctx->fail(rc, std::string("ar_decode_launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+      ctx->launches++;
+      if (rc == M5_OK && ar_sample(sc, ctx->stream) != M5_OK) rc = ctx->fail(M5_ERR_CUDA, "ar_sample failed");
+      ctx->launches++;
+    }
     g_use_pdl = false;
     cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
     step_launches = ctx->launches - before;

@@ -1,0 +1,640 @@
+// Fused, persistent AR decode step: ONE cooperative kernel runs all transformer layers of a KV-cached CodecLM step for
+// B <= 32 utterances (reference loop body: mars5/ar_generate.py:62-71 -> model.py:95-141 -> nn_future.py:235-274,
+// 297-333,369-398), followed by the fused sampler kernel (sampler.cu).
+//
+// Grid = one CTA per SM (256 threads, 8 warps), resident for the whole step; phases are separated by a device-wide
+// barrier (5 per layer):
+//   P0        x = embed(last token) (+ per-row sum-of-squares partials)
+//   per layer:
+//     P1  QKV projection      X = fp16(RMSNorm(x) * gamma) staged per CTA, weights streamed once (ld.global.nc, 128-bit)
+//                             into mma.sync fragments, split-K partials, last CTA of a row tile reduces -> qkv fp32
+//     P2  attention           one (utterance, head, 256-key split) per WARP: q / new k get RoPE from the fp32 qkv row, the new
+//                             k, v are appended to the fp16 KV cache, the cached keys / values arrive as 32-key TMA tiles
+//                             (cp.async.bulk.tensor, 3-deep per-warp mbarrier ring in shared memory), online softmax in
+//                             fp32, per-split (m, l, acc) partials
+//     P3  WO projection       X = merged attention output (split partials merged while staging); epilogue x += ...,
+//                             and the row sums of squares the next RMSNorm needs (per 128-column tile, fixed order)
+//     P4  W1|W3 + SwiGLU      X = fp16(RMSNorm(x) * gamma); epilogue silu(w1 x) * (w3 x) -> g fp16
+//     P5  W2 projection       X = g; epilogue x += ..., sums of squares
+//   final     vocabulary projection of RMSNorm(x) -> logits fp32
+// The first weight fragments (or KV tiles) of the NEXT phase are requested before a CTA waits at the barrier, so HBM
+// keeps streaming across phase boundaries.  Everything a later phase reads that an earlier phase wrote goes through L2
+// (ld.global.cg / cp.async.cg / TMA), never through the non-coherent L1.
+// Algorithmic bytes per step: the fp16 weights once (1.37 GB) + every cached K/V once.
+#include <cuda.h>
+
+#include "ar_decode.h"
+#include "ptx.cuh"
+
+namespace m5 {
+
+static constexpr int AD_THREADS = 256, AD_WARPS = 8;
+static constexpr int AD_ROWS = 128;      // weight rows per GEMM work item (16 per warp)
+static constexpr int AD_UNROLL = 6;      // 32-column weight chunks in flight per warp
+static constexpr int AD_KT = 32;         // keys per TMA tile
+static constexpr int AD_NST = 3;         // TMA stages per warp
+static constexpr int AD_STAGE_BYTES = 2 * AD_KT * 128;                      // K tile + V tile
+static constexpr int AD_SPLIT = 256;     // keys per attention work item
+static constexpr int AD_PART = 68;       // floats per split partial: m, l, pad, pad, acc[64] (16-byte aligned rows)
+static constexpr int AD_SMEM_KV = AD_WARPS * AD_NST * AD_STAGE_BYTES;        // 192 KB
+static constexpr int AD_SMEM = AD_SMEM_KV + 1024;                            // + mbarriers, tickets
+
+M5_DEVINL uint4 ad_ldg_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+M5_DEVINL unsigned ad_ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Device-wide barrier for a co-resident grid (cooperative launch): monotonic arrival counter, zeroed by the host before
+// every launch.  `epoch` is the number of arrivals that completes the barrier this CTA is about to join.
+M5_DEVINL void grid_sync(unsigned* bar, unsigned& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += gridDim.x;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    if (ad_ld_acquire(bar) < epoch) {
+      const uint64_t t0 = global_timer_ns();
+      uint32_t spins = 0;
+      while (ad_ld_acquire(bar) < epoch) {
+        if ((++spins & 0x3FF) == 0 && global_timer_ns() - t0 > 2000000000ull) {
+          printf("m5: ar_decode grid barrier timed out (block %d, epoch %u)\n", blockIdx.x, epoch);
+          __trap();
+        }
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM phases
+struct WFrag { uint4 a[AD_UNROLL], b[AD_UNROLL]; };
+
+// item -> (row tile, K slice); rows of W this lane streams
+struct GemmItem {
+  int tile, ks, n0, kbase;
+  const __half *w0, *w1;
+};
+M5_DEVINL GemmItem gemm_item(const ArGemm& g, int item, int warp, int lane) {
+  GemmItem it;
+  it.tile = item / g.ksplit; it.ks = item - it.tile * g.ksplit;
+  it.n0 = it.tile * AD_ROWS + warp * 16;
+  it.kbase = it.ks * g.kslice;
+  const int gq = lane >> 2, t = lane & 3;
+  const int r0 = min(it.n0 + gq, g.N - 1), r1 = min(it.n0 + gq + 8, g.N - 1);
+  it.w0 = g.W + (size_t)r0 * g.K + it.kbase + 8 * t;
+  it.w1 = g.W + (size_t)r1 * g.K + it.kbase + 8 * t;
+  return it;
+}
+M5_DEVINL void gemm_fetch(const ArGemm& g, const GemmItem& it, int c0, WFrag& f) {
+  const int chunks = g.kslice / 32;
+#pragma unroll
+  for (int u = 0; u < AD_UNROLL; ++u) {
+    if (c0 + u < chunks) {
+      f.a[u] = ad_ldg_stream(it.w0 + (c0 + u) * 32);
+      f.b[u] = ad_ldg_stream(it.w1 + (c0 + u) * 32);
+    }
+  }
+}
+
+enum { X_NORM = 0, X_ATTN = 1, X_F16 = 2 };        // how the activation slice of a GEMM phase is produced
+enum { EPI_STORE = 0, EPI_RESID = 1, EPI_SWIGLU = 2 };
+
+// Stages X[:, kbase : kbase + kslice] as fp16 rows with a 64-byte skew (conflict-free 16-byte reads).
+template <int NT, int XSRC>
+M5_DEVINL void stage_x(const ArDecodeParams& p, const ArGemm& g, int kbase, const float* gamma, uint8_t* xs, float* s_scale) {
+  constexpr int BT = 8 * NT;
+  const int tid = threadIdx.x;
+  const int xstride = g.kslice * 2 + 64;
+  if constexpr (XSRC == X_NORM) {
+    // RMSNorm (nn_future.py:301-312): x * rsqrt(mean(x^2) + eps) * weight, the mean from the per-tile partial sums
+    if (tid < BT) {
+      float ss = 0.f;
+      if (tid < p.B)
+        for (int t = 0; t < p.ssq_tiles; ++t) ss += __ldcg(p.ssq + t * 32 + tid);
+      s_scale[tid] = rsqrtf(ss / (float)p.D + p.eps);
+    }
+    __syncthreads();
+    const int quads = g.kslice / 4;
+    for (int i = tid; i < BT * quads; i += AD_THREADS) {
+      const int row = i / quads, c = (i - row * quads) * 4;
+      uint2 o = make_uint2(0u, 0u);
+      if (row < p.B) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(p.x + (size_t)row * p.D + kbase + c));
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + kbase + c));
+        const float sc = s_scale[row];
+        o.x = pack_half2((v.x * sc) * gm.x, (v.y * sc) * gm.y);
+        o.y = pack_half2((v.z * sc) * gm.z, (v.w * sc) * gm.w);
+      }
+      *reinterpret_cast<uint2*>(xs + (size_t)row * xstride + c * 2) = o;
+    }
+  } else if constexpr (XSRC == X_ATTN) {
+    // merge of the split-KV partials (m, l, acc[64]) in split order: one (row, head) per 32 lanes, 2 columns per lane
+    const int warp = tid >> 5, lane = tid & 31;
+    const int heads = g.kslice / 64, h0 = kbase / 64;
+    for (int i = warp; i < BT * heads; i += AD_WARPS) {
+      const int row = i / heads, hh = i - row * heads;
+      float ox = 0.f, oy = 0.f;
+      if (row < p.B && !(p.done && p.done[row])) {
+        const float* sp = p.attn_part + ((size_t)(row * p.H + h0 + hh) * p.n_split) * AD_PART;
+        const int L = p.kv_len[row];
+        const int ns = min(p.n_split, (L + AD_SPLIT - 1) / AD_SPLIT);
+        float M = -INFINITY;
+        for (int s = 0; s < ns; ++s) M = fmaxf(M, __ldcg(sp + s * AD_PART));
+        float Ls = 0.f;
+        for (int s = 0; s < ns; ++s) {
+          const float* q = sp + s * AD_PART;
+          const float ms = __ldcg(q);
+          if (ms == -INFINITY) continue;
+          const float c = exp2f(ms - M);
+          const float2 a = __ldcg(reinterpret_cast<const float2*>(q + 4 + 2 * lane));
+          Ls += __ldcg(q + 1) * c;
+          ox += a.x * c;
+          oy += a.y * c;
+        }
+        const float inv = Ls > 0.f ? 1.f / Ls : 0.f;
+        ox *= inv; oy *= inv;
+      }
+      *reinterpret_cast<uint32_t*>(xs + (size_t)row * xstride + (hh * 64 + 2 * lane) * 2) = pack_half2(ox, oy);
+    }
+  } else {
+    const int vec_per_row = g.kslice / 8;
+    for (int i = tid; i < BT * vec_per_row; i += AD_THREADS) {
+      const int row = i / vec_per_row, v = i - row * vec_per_row;
+      const bool ok = row < p.B;
+      cp_async16(xs + (size_t)row * xstride + v * 16, ok ? (p.g16 + (size_t)row * g.K + kbase + v * 8) : p.g16, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+  }
+  __syncthreads();
+}
+
+// One GEMM phase: this CTA's work items (item = cta, cta + grid, ...).  `pre` holds the first weight fragments of the
+// first item when `have_pre` (requested before the preceding grid barrier).
+template <int NT, int XSRC, int EPI>
+M5_DEVINL void gemm_phase(const ArDecodeParams& p, const ArGemm& g, const float* gamma, float* out_f32, int ldo, uint8_t* smem,
+                          WFrag& pre, bool have_pre) {
+  constexpr int BT = 8 * NT;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, t = lane & 3;
+  uint8_t* xs = smem;
+  float* s_scale = reinterpret_cast<float*>(smem + AD_SMEM_KV + 512);   // [32]
+  int* s_ticket = reinterpret_cast<int*>(smem + AD_SMEM_KV + 512 + 128);
+  const int n_items = g.tiles * g.ksplit;
+  const int chunks = g.kslice / 32;
+  const int xstride = g.kslice * 2 + 64;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const GemmItem it = gemm_item(g, item, warp, lane);
+    if (!have_pre) gemm_fetch(g, it, 0, pre);
+    have_pre = false;
+    stage_x<NT, XSRC>(p, g, it.kbase, gamma, xs, s_scale);
+    float acc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    for (int c0 = 0; c0 < chunks; c0 += AD_UNROLL) {
+      if (c0 > 0) gemm_fetch(g, it, c0, pre);
+#pragma unroll
+      for (int u = 0; u < AD_UNROLL; ++u) {
+        const int c = c0 + u;
+        if (c < chunks) {
+          const uint32_t a1[4] = {pre.a[u].x, pre.b[u].x, pre.a[u].y, pre.b[u].y};
+          const uint32_t a2[4] = {pre.a[u].z, pre.b[u].z, pre.a[u].w, pre.b[u].w};
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const uint4 x = *reinterpret_cast<const uint4*>(xs + (size_t)(nt * 8 + gq) * xstride + (c * 32 + 8 * t) * 2);
+            mma_16816(acc[nt], a1, x.x, x.y);
+            mma_16816(acc[nt], a2, x.z, x.w);
+          }
+        }
+      }
+    }
+    // ---- partial tile -> scratch[item][b][row]
+    float* part = p.scratch + (size_t)item * (32 * AD_ROWS);
+    const int rl = warp * 16 + gq;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int b0 = nt * 8 + 2 * t;
+      __stcg(part + (size_t)b0 * AD_ROWS + rl, acc[nt][0]);
+      __stcg(part + (size_t)(b0 + 1) * AD_ROWS + rl, acc[nt][1]);
+      __stcg(part + (size_t)b0 * AD_ROWS + rl + 8, acc[nt][2]);
+      __stcg(part + (size_t)(b0 + 1) * AD_ROWS + rl + 8, acc[nt][3]);
+    }
+    __threadfence();
+    __syncthreads();   // also: every warp is done with the staged X before the next item overwrites it
+    if (tid == 0) *s_ticket = atomicAdd(p.counters + it.tile, 1);
+    __syncthreads();
+    if (*s_ticket != g.ksplit - 1) continue;
+    // ---- last CTA of this row tile: ordered reduction over the K slices + epilogue
+    __threadfence();
+    if (tid == 0) p.counters[it.tile] = 0;
+    const float* base = p.scratch + (size_t)(it.tile * g.ksplit) * (32 * AD_ROWS);
+    const int nrow0 = it.tile * AD_ROWS;
+    if constexpr (EPI == EPI_SWIGLU) {
+      for (int i = tid; i < BT * (AD_ROWS / 2); i += AD_THREADS) {
+        const int b = i / (AD_ROWS / 2), pr = i - b * (AD_ROWS / 2);
+        const int n = nrow0 + 2 * pr;
+        if (b >= p.B || n + 1 >= g.N) continue;
+        float a = 0.f, c = 0.f;
+        for (int s = 0; s < g.ksplit; ++s) {
+          const float2 v2 = __ldcg(reinterpret_cast<const float2*>(base + (size_t)s * (32 * AD_ROWS) + (size_t)b * AD_ROWS + 2 * pr));
+          a += v2.x;
+          c += v2.y;
+        }
+        p.g16[(size_t)b * (g.N / 2) + (n >> 1)] = __float2half_rn((a / (1.f + __expf(-a))) * c);
+      }
+    } else {
+      // warp w owns batch rows w, w + 8, ...; a lane owns 4 consecutive weight rows (= output columns) of the tile
+      for (int b = warp; b < BT; b += AD_WARPS) {
+        if (b >= p.B) continue;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < g.ksplit; ++s) {
+          const float4 q = __ldcg(reinterpret_cast<const float4*>(base + (size_t)s * (32 * AD_ROWS) + (size_t)b * AD_ROWS + 4 * lane));
+          v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+        }
+        const int n = nrow0 + 4 * lane;
+        float* o = out_f32 + (size_t)b * ldo + n;
+        float sq = 0.f;
+        if (n + 3 < g.N && (ldo & 3) == 0) {
+          if constexpr (EPI == EPI_RESID) {
+            const float4 r = __ldcg(reinterpret_cast<const float4*>(o));
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            sq = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          }
+          __stcg(reinterpret_cast<float4*>(o), v);
+        } else {
+          const float e[4] = {v.x, v.y, v.z, v.w};
+          for (int j = 0; j < 4; ++j) {
+            if (n + j < g.N) {
+              float w = e[j];
+              if constexpr (EPI == EPI_RESID) { w += __ldcg(o + j); sq += w * w; }
+              __stcg(o + j, w);
+            }
+          }
+        }
+        if constexpr (EPI == EPI_RESID) {
+          sq = warp_sum(sq);
+          if (lane == 0) __stcg(p.ssq + it.tile * 32 + b, sq);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ attention phase
+struct AttnItem {
+  int b, h, s, k0, n_cache, has_new, row0;   // n_cache: cached keys of this split; row0: first cache row of the split
+};
+M5_DEVINL bool attn_item(const ArDecodeParams& p, int layer, int idx, AttnItem& it) {
+  const int per_b = p.H * p.n_split;
+  it.b = idx / per_b;
+  const int r = idx - it.b * per_b;
+  it.h = r / p.n_split;
+  it.s = r - it.h * p.n_split;
+  if (p.done && p.done[it.b]) return false;
+  const int L = p.kv_len[it.b];               // positions 0 .. L-2 are cached, L-1 is the token of this step
+  it.k0 = it.s * AD_SPLIT;
+  if (it.k0 >= L) return false;
+  it.n_cache = min(AD_SPLIT, L - 1 - it.k0);
+  it.has_new = (L - 1 < it.k0 + AD_SPLIT) ? 1 : 0;
+  it.row0 = (layer * p.B + it.b) * p.Wc + it.k0;
+  return true;
+}
+// walks the (item, tile) sequence of one warp for one layer
+struct TileIter {
+  int idx, t, n_tiles, row0, h;
+  bool valid;
+};
+M5_DEVINL void tile_seek(const ArDecodeParams& p, int layer, int total, int stride, TileIter& ti) {
+  ti.valid = false;
+  while (ti.idx < total) {
+    AttnItem it;
+    if (attn_item(p, layer, ti.idx, it) && it.n_cache > 0) {
+      ti.n_tiles = (it.n_cache + AD_KT - 1) / AD_KT; ti.row0 = it.row0; ti.h = it.h; ti.t = 0; ti.valid = true;
+      return;
+    }
+    ti.idx += stride;
+  }
+}
+M5_DEVINL void tile_next(const ArDecodeParams& p, int layer, int total, int stride, TileIter& ti) {
+  if (++ti.t < ti.n_tiles) return;
+  ti.idx += stride;
+  tile_seek(p, layer, total, stride, ti);
+}
+M5_DEVINL void tile_issue(const CUtensorMap* tk, const CUtensorMap* tv, uint8_t* ring, uint64_t* bars, uint32_t seq, const TileIter& ti) {
+  const int st = seq % AD_NST;
+  uint8_t* dst = ring + st * AD_STAGE_BYTES;
+  mbar_arrive_expect_tx(bars + st, AD_STAGE_BYTES);
+  tma_load_2d(dst, tk, bars + st, ti.h * 64, ti.row0 + ti.t * AD_KT);
+  tma_load_2d(dst + AD_KT * 128, tv, bars + st, ti.h * 64, ti.row0 + ti.t * AD_KT);
+}
+
+struct AttnWarpState {
+  uint32_t issued, consumed;   // tiles since kernel start (stage = seq % NST, parity = (seq / NST) & 1)
+  TileIter prod;
+};
+
+M5_DEVINL void attn_prefetch(const ArDecodeParams& p, const CUtensorMap* tk, const CUtensorMap* tv, int layer, uint8_t* ring,
+                             uint64_t* bars, AttnWarpState& st) {
+  const int lane = threadIdx.x & 31, gw = blockIdx.x * AD_WARPS + (threadIdx.x >> 5);
+  const int total = p.B * p.H * p.n_split, stride = gridDim.x * AD_WARPS;
+  st.prod.idx = gw;
+  tile_seek(p, layer, total, stride, st.prod);
+  while (st.prod.valid && st.issued - st.consumed < AD_NST) {
+    if (lane == 0) tile_issue(tk, tv, ring, bars, st.issued, st.prod);
+    ++st.issued;
+    tile_next(p, layer, total, stride, st.prod);
+  }
+}
+
+M5_DEVINL void attn_phase(const ArDecodeParams& p, const ArLayerDev& lw, const CUtensorMap* tk, const CUtensorMap* tv, int layer,
+                          uint8_t* ring, uint64_t* bars, AttnWarpState& st) {
+  const int lane = threadIdx.x & 31, gw = blockIdx.x * AD_WARPS + (threadIdx.x >> 5);
+  const int sub = lane & 7, grp = lane >> 3;
+  const int total = p.B * p.H * p.n_split, stride = gridDim.x * AD_WARPS;
+  const int D = p.D;
+  const float sl2 = 0.125f * 1.4426950408889634f;
+  (void)lw;
+  for (int idx = gw; idx < total; idx += stride) {
+    AttnItem it;
+    if (!attn_item(p, layer, idx, it)) continue;
+    const int L = p.kv_len[it.b];
+    const float* qkv = p.qkv + (size_t)it.b * 3 * D + it.h * 64 + sub * 8;
+    // q of this head: fp16 projection output, RoPE at position L-1 in fp32, rounded to fp16 (nn_future.py:186-191)
+    float q[8], cs[4], sn[4];
+    {
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(qkv)), c = __ldcg(reinterpret_cast<const float4*>(qkv + 4));
+      const float r[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float ang = (float)(L - 1) * __ldg(p.inv_freq + sub * 4 + i);
+        sincosf(ang, &sn[i], &cs[i]);
+        const float2 h = __half22float2(__floats2half2_rn(r[2 * i], r[2 * i + 1]));
+        const float2 o = __half22float2(__floats2half2_rn(h.x * cs[i] - h.y * sn[i], h.x * sn[i] + h.y * cs[i]));
+        q[2 * i] = o.x; q[2 * i + 1] = o.y;
+      }
+    }
+    float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    auto fold = [&](const uint4& kv, const uint4& vv, bool ok) {
+      const __half2* kh = reinterpret_cast<const __half2*>(&kv);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(kh[i]); s += q[2 * i] * f.x + q[2 * i + 1] * f.y; }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (ok) {
+        s *= sl2;
+        const float mn = fmaxf(m, s);
+        const float c = exp2f(m - mn), pe = exp2f(s - mn);
+        l = l * c + pe;
+        const __half2* vh = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(vh[i]);
+          acc[2 * i] = acc[2 * i] * c + pe * f.x;
+          acc[2 * i + 1] = acc[2 * i + 1] * c + pe * f.y;
+        }
+        m = mn;
+      }
+    };
+    const int n_tiles = (it.n_cache + AD_KT - 1) / AD_KT;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int sg = st.consumed % AD_NST;
+      mbar_wait(bars + sg, (st.consumed / AD_NST) & 1);
+      const uint8_t* sk = ring + sg * AD_STAGE_BYTES;
+      const uint8_t* sv = sk + AD_KT * 128;
+      const int kvalid = it.n_cache - t * AD_KT;   // keys of this tile that exist (>= 1)
+#pragma unroll
+      for (int u = 0; u < AD_KT / 4; ++u) {
+        const int kr = u * 4 + grp;
+        const uint4 kv = *reinterpret_cast<const uint4*>(sk + kr * 128 + sub * 16);
+        const uint4 vv = *reinterpret_cast<const uint4*>(sv + kr * 128 + sub * 16);
+        fold(kv, vv, kr < kvalid);
+      }
+      __syncwarp();            // every lane has read the stage: it may be refilled
+      ++st.consumed;
+      if (st.prod.valid) {
+        if (lane == 0) tile_issue(tk, tv, ring, bars, st.issued, st.prod);
+        ++st.issued;
+        tile_next(p, layer, total, stride, st.prod);
+      }
+    }
+    if (it.has_new) {
+      // K / V of the token fed in this step: rounded to fp16 like the projection output, K with RoPE; appended to the cache
+      // (nn_future.py:248-252) and folded into the softmax straight from registers
+      const float4 ka = __ldcg(reinterpret_cast<const float4*>(qkv + D)), kb = __ldcg(reinterpret_cast<const float4*>(qkv + D + 4));
+      const float4 va = __ldcg(reinterpret_cast<const float4*>(qkv + 2 * D)), vb = __ldcg(reinterpret_cast<const float4*>(qkv + 2 * D + 4));
+      const float kr[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+      uint4 kn, vn;
+      uint32_t* kw = reinterpret_cast<uint32_t*>(&kn);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 h = __half22float2(__floats2half2_rn(kr[2 * i], kr[2 * i + 1]));
+        kw[i] = pack_half2(h.x * cs[i] - h.y * sn[i], h.x * sn[i] + h.y * cs[i]);
+      }
+      vn = make_uint4(pack_half2(va.x, va.y), pack_half2(va.z, va.w), pack_half2(vb.x, vb.y), pack_half2(vb.z, vb.w));
+      if (grp == 0) {
+        const size_t coff = ((size_t)(layer * p.B + it.b) * p.Wc + (L - 1)) * D + it.h * 64 + sub * 8;
+        *reinterpret_cast<uint4*>(p.kc + coff) = kn;
+        *reinterpret_cast<uint4*>(p.vc + coff) = vn;
+      }
+      fold(kn, vn, grp == 0);
+    }
+    // merge the 4 key groups of the warp (fixed order), write the split partial (m, l, acc[64])
+    float M = fmaxf(fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8)), fmaxf(__shfl_xor_sync(0xffffffffu, m, 16), __shfl_xor_sync(0xffffffffu, m, 24)));
+    const float c = (m == -INFINITY) ? 0.f : exp2f(m - M);
+    l *= c;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= c;
+    l += __shfl_xor_sync(0xffffffffu, l, 8);
+    l += __shfl_xor_sync(0xffffffffu, l, 16);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+      acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+    }
+    float* sp = p.attn_part + ((size_t)(it.b * p.H + it.h) * p.n_split + it.s) * AD_PART;
+    if (lane == 0) { __stcg(sp, M); __stcg(sp + 1, l); }
+    if (grp == 0) {
+      __stcg(reinterpret_cast<float4*>(sp + 4 + sub * 8), make_float4(acc[0], acc[1], acc[2], acc[3]));
+      __stcg(reinterpret_cast<float4*>(sp + 4 + sub * 8 + 4), make_float4(acc[4], acc[5], acc[6], acc[7]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <int NT>
+__global__ void __launch_bounds__(AD_THREADS, 1)
+ar_decode_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v, ArDecodeParams p) {
+  extern __shared__ __align__(1024) uint8_t ad_smem[];
+  uint8_t* smem = ad_smem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AD_SMEM_KV) + warp * AD_NST;   // this warp's stage barriers
+  uint8_t* ring = smem + warp * (AD_NST * AD_STAGE_BYTES);
+  if (lane == 0) {
+    for (int s = 0; s < AD_NST; ++s) mbar_init(bars + s, 1);
+    fence_barrier_init();
+  }
+  if (tid == 0) { tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); }
+  __syncthreads();
+  unsigned epoch = 0;
+  AttnWarpState ast;
+  ast.issued = ast.consumed = 0;
+  ast.prod.valid = false;
+  WFrag wf;
+
+  // ---- P0: x = embed[last token] (nn.Embedding is not autocast: fp32 value of the fp16-exact weight) + sums of squares
+  {
+    const int tiles = p.ssq_tiles;   // ceil(D / 128)
+    for (int tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
+      for (int b = warp; b < p.B; b += AD_WARPS) {
+        const int tok = p.ids[(size_t)b * p.ids_stride + p.tok_len[b] - 1];
+        const int c = tl * 128 + lane * 4;
+        float2 a = make_float2(0.f, 0.f), bb = make_float2(0.f, 0.f);
+        if (c < p.D) {
+          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p.embed + (size_t)tok * p.D + c));
+          a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)); bb = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+          __stcg(reinterpret_cast<float4*>(p.x + (size_t)b * p.D + c), make_float4(a.x, a.y, bb.x, bb.y));
+        }
+        const float sq = warp_sum(a.x * a.x + a.y * a.y + bb.x * bb.x + bb.y * bb.y);
+        if (lane == 0) __stcg(p.ssq + tl * 32 + b, sq);
+      }
+    }
+  }
+  {
+    const ArLayerDev& l0 = p.layers[0];
+    ArGemm g = p.g_qkv; g.W = l0.wqkv;
+    if ((int)blockIdx.x < g.tiles * g.ksplit) gemm_fetch(g, gemm_item(g, blockIdx.x, warp, lane), 0, wf);
+  }
+  grid_sync(p.gbar, epoch);
+
+  for (int layer = 0; layer < p.n_layers; ++layer) {
+    const ArLayerDev& lw = p.layers[layer];
+    ArGemm g;
+    // ---- P1: qkv = Wqkv . rmsnorm(x)
+    g = p.g_qkv; g.W = lw.wqkv;
+    gemm_phase<NT, X_NORM, EPI_STORE>(p, g, lw.attn_norm, p.qkv, 3 * p.D, smem, wf, (int)blockIdx.x < g.tiles * g.ksplit);
+    __syncthreads();
+    attn_prefetch(p, &tmap_k, &tmap_v, layer, ring, bars, ast);
+    grid_sync(p.gbar, epoch);
+    // ---- P2: attention over the cache + the new token
+    attn_phase(p, lw, &tmap_k, &tmap_v, layer, ring, bars, ast);
+    g = p.g_wo; g.W = lw.wo;
+    const bool pre_wo = (int)blockIdx.x < g.tiles * g.ksplit;
+    if (pre_wo) gemm_fetch(g, gemm_item(g, blockIdx.x, warp, lane), 0, wf);
+    grid_sync(p.gbar, epoch);
+    // ---- P3: x += Wo . attn
+    gemm_phase<NT, X_ATTN, EPI_RESID>(p, g, nullptr, p.x, p.D, smem, wf, pre_wo);
+    g = p.g_w13; g.W = lw.w13;
+    const bool pre_13 = (int)blockIdx.x < g.tiles * g.ksplit;
+    if (pre_13) gemm_fetch(g, gemm_item(g, blockIdx.x, warp, lane), 0, wf);
+    grid_sync(p.gbar, epoch);
+    // ---- P4: g = silu(W1 . h) * (W3 . h), h = rmsnorm(x)
+    gemm_phase<NT, X_NORM, EPI_SWIGLU>(p, g, lw.ffn_norm, nullptr, 0, smem, wf, pre_13);
+    g = p.g_w2; g.W = lw.w2;
+    const bool pre_2 = (int)blockIdx.x < g.tiles * g.ksplit;
+    if (pre_2) gemm_fetch(g, gemm_item(g, blockIdx.x, warp, lane), 0, wf);
+    grid_sync(p.gbar, epoch);
+    // ---- P5: x += W2 . g
+    gemm_phase<NT, X_F16, EPI_RESID>(p, g, nullptr, p.x, p.D, smem, wf, pre_2);
+    if (layer + 1 < p.n_layers) { g = p.g_qkv; g.W = p.layers[layer + 1].wqkv; }
+    else { g = p.g_out; }
+    if ((int)blockIdx.x < g.tiles * g.ksplit) gemm_fetch(g, gemm_item(g, blockIdx.x, warp, lane), 0, wf);
+    grid_sync(p.gbar, epoch);
+  }
+  // ---- logits = Wout . rmsnorm(x)
+  gemm_phase<NT, X_NORM, EPI_STORE>(p, p.g_out, p.final_norm, p.logits, p.V, smem, wf, (int)blockIdx.x < p.g_out.tiles * p.g_out.ksplit);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static void pick(ArGemm& g, int N, int K, int grid) {
+  g.N = N; g.K = K; g.tiles = (N + AD_ROWS - 1) / AD_ROWS;
+  const int kb = K / 64;
+  int best = 1;
+  double best_u = -1e9;
+  for (int s = 1; s <= kb && s <= 16; ++s) {
+    if (kb % s) continue;
+    const int ksl = K / s;
+    if (ksl < 128 || ksl > 1024) continue;
+    const int items = g.tiles * s;
+    // SM utilisation of the phase minus a price per extra K slice (partial-sum traffic, one staging + ticket per item)
+    const double u = (double)items / ((double)((items + grid - 1) / grid) * grid) - 0.02 * s;
+    if (u > best_u) { best_u = u; best = s; }
+  }
+  if (best_u < -1e8) {   // K too small / too large for the limits above: smallest admissible split
+    for (int s = 1; s <= kb; ++s) if (kb % s == 0 && K / s <= 1024) { best = s; break; }
+  }
+  g.ksplit = best; g.kslice = K / best;
+}
+
+int ar_decode_plan(ArDecodeParams& p, int num_sms) {
+  if (p.B <= 0 || p.B > 32 || p.D % 64 != 0 || p.F % 64 != 0 || p.D != p.H * 64) return M5_ERR_ARG;
+  pick(p.g_qkv, 3 * p.D, p.D, num_sms);
+  pick(p.g_wo, p.D, p.D, num_sms);
+  pick(p.g_w13, 2 * p.F, p.D, num_sms);
+  pick(p.g_w2, p.D, p.F, num_sms);
+  pick(p.g_out, p.V, p.D, num_sms);
+  if (p.g_wo.kslice % 64 != 0) return M5_ERR_ARG;   // whole heads per K slice (attention merge while staging)
+  p.ssq_tiles = (p.D + 127) / 128;
+  return M5_OK;
+}
+size_t ar_decode_scratch_floats(const ArDecodeParams& p) {
+  int mx = 0;
+  for (const ArGemm* g : {&p.g_qkv, &p.g_wo, &p.g_w13, &p.g_w2, &p.g_out}) mx = std::max(mx, g->tiles * g->ksplit);
+  return (size_t)mx * 32 * AD_ROWS;
+}
+int ar_decode_max_tiles(const ArDecodeParams& p) {
+  int mx = 0;
+  for (const ArGemm* g : {&p.g_qkv, &p.g_wo, &p.g_w13, &p.g_w2, &p.g_out}) mx = std::max(mx, g->tiles);
+  return mx;
+}
+int ar_decode_splits_for(int max_kv) { return (max_kv + AD_SPLIT - 1) / AD_SPLIT; }
+size_t ar_decode_attn_floats(int B, int H, int n_split) { return (size_t)B * H * n_split * AD_PART; }
+
+typedef CUresult (*AdEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int ad_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols) {
+  static AdEncodeFn fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qr) != cudaSuccess || !q) return M5_ERR_CUDA;
+    fn = reinterpret_cast<AdEncodeFn>(q);
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {64, AD_KT};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? M5_OK : M5_ERR_CUDA;
+}
+
+int ar_decode_launch(const ArDecodeParams& p, int num_sms, cudaStream_t stream) {
+  CUtensorMap tk, tv;
+  const uint64_t rows = (uint64_t)p.n_layers * p.B * p.Wc;
+  if (ad_tmap(&tk, p.kc, rows, p.D) != M5_OK || ad_tmap(&tv, p.vc, rows, p.D) != M5_OK) return M5_ERR_CUDA;
+  void (*kern)(CUtensorMap, CUtensorMap, ArDecodeParams) =
+      p.B <= 8 ? ar_decode_kernel<1> : (p.B <= 16 ? ar_decode_kernel<2> : ar_decode_kernel<4>);
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AD_SMEM) != cudaSuccess) return M5_ERR_CUDA;
+  if (cudaMemsetAsync(p.gbar, 0, sizeof(unsigned), stream) != cudaSuccess) return M5_ERR_CUDA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(num_sms); cfg.blockDim = dim3(AD_THREADS); cfg.dynamicSmemBytes = AD_SMEM; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: the device-wide barrier cannot deadlock
+  at[0].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, tk, tv, p) == cudaSuccess ? M5_OK : M5_ERR_CUDA;
+}
+
+}  // namespace m5

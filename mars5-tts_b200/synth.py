@@ -110,7 +110,7 @@ def make_nar_state(size, seed=1):
     return sd
 
 
-def make_vocos_state(size, seed=2, n_fft=1280, n_bw=4):
+def make_vocos_state(size, seed=2, n_fft=1280, n_bw=4, n_codebooks=16):
     """Vocos encodec-24khz state dict with vocos' own module names (fp32 values, not fp16-exact, like the real one)."""
     g = torch.Generator().manual_seed(seed)
     feat, dim, inter = size["voc_feat"], size["voc_dim"], size["voc_inter"]
@@ -118,7 +118,8 @@ def make_vocos_state(size, seed=2, n_fft=1280, n_bw=4):
     def rn(*shape, std=1.0):
         return torch.randn(*shape, generator=g) * std
 
-    sd = {"feature_extractor.codebook_weights": rn(8 * 1024, feat, std=0.5)}
+    # like the released checkpoint: the codebooks of the maximum bandwidth (12 kbps = 16 x 1024 rows), 8 of which are used
+    sd = {"feature_extractor.codebook_weights": rn(n_codebooks * 1024, feat, std=0.5)}
     sd["backbone.embed.weight"] = rn(dim, feat, 7, std=1.0 / (7 * feat) ** 0.5)
     sd["backbone.embed.bias"] = rn(dim, std=0.02)
     sd["backbone.norm.scale.weight"] = 1.0 + rn(n_bw, dim, std=0.05)

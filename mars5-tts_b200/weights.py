@@ -39,7 +39,13 @@ def dims_from_state(ar_sd, nar_sd, voc_sd, text_vocab_len):
         d["voc_nfft"] = voc_sd["head.out.weight"].shape[0] - 2
         d["voc_hop"] = d["voc_nfft"] // 4
         d["voc_n_bw"] = voc_sd["backbone.norm.scale.weight"].shape[0]
-        d["voc_codebook"] = voc_sd["feature_extractor.codebook_weights"].shape[0] // d["n_quant"]
+        # vocos' codes_to_features offsets codebook q by q * quantizer.bins (= 1024 Encodec codes = n_classes - 1); the
+        # released charactr/vocos-encodec-24khz table concatenates the codebooks of the MAXIMUM bandwidth (16 x 1024 rows),
+        # of which an 8-codebook input touches the first 8 x 1024
+        d["voc_codebook"] = d["n_classes"] - 1
+        rows = voc_sd["feature_extractor.codebook_weights"].shape[0]
+        if rows < d["n_quant"] * d["voc_codebook"]:
+            raise ValueError(f"vocos codebook_weights has {rows} rows, need at least n_quant * bins = {d['n_quant'] * d['voc_codebook']}")
     return d
 
 

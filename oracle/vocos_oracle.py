@@ -16,8 +16,8 @@ import torch.nn.functional as F
 def vocos_forward(sd, codes, bandwidth_id, n_fft=1280, hop=320, return_spec=False):
     """codes (N, 8) -> waveform (320 * N,)."""
     N, Q = codes.shape
-    cb = sd["feature_extractor.codebook_weights"]  # (Q*1024, 128)
-    bins = cb.shape[0] // Q
+    cb = sd["feature_extractor.codebook_weights"]  # (n_codebooks_max * 1024, 128): 16 x 1024 rows in the released checkpoint
+    bins = 1024  # encodec.quantizer.bins -- vocos offsets codebook q by q * bins regardless of how many codebooks the table holds
     feats = sum(cb[codes[:, q] + q * bins] for q in range(Q))  # (N, 128)
     x = feats.T[None]  # (1, 128, N)
     x = F.conv1d(x, sd["backbone.embed.weight"], sd["backbone.embed.bias"], padding=3)
