@@ -91,6 +91,7 @@ typedef struct {
   int32_t eos_id;       /* len(texttok.vocab) + speechtok '<|endofspeech|>' (ar_generate.py:47) */
   int32_t force_len;    /* benchmark only: >0 masks EOS until this many tokens were generated, then forces it */
   int32_t sync_every;   /* host polls the all-done flag every this many steps (default 16) */
+  float typical_p;      /* InferenceConfig.typical_p: locally-typical mass tau (samplers.py:96-122); > 0.999 (or 0) disables */
 } m5_ar_cfg;
 
 /*
@@ -123,6 +124,12 @@ typedef struct {
   /* optional HOST tables [4][T]: log_alpha, log_1_min_alpha, log_cumprod_alpha, log_1_min_cumprod_alpha
    * (MultinomialDiffusion.__init__, diffuser.py:76-95); NULL -> computed inside the library */
   const float* schedule;
+  /* RePaint resampling (get_schedule, diffuser.py:318-333; DSH.jump_len / jump_n_sample): 0 or 1 = none (what
+   * inference.py:291 uses).  With jumps the reverse loop is interleaved with forward steps x_t -> x_{t+1} ~
+   * q_pred_one_timestep (diffuser.py:119-134,336-342).  scaled_forward = DSH.enable_kevin_scaled_inference: the
+   * reference's q_pred_one_timestep_scaled (diffuser.py:136-159) raises a broadcasting error for every S != 8, so
+   * scaled_forward != 0 together with jumps is rejected with M5_ERR_ARG. */
+  int32_t jump_len, jump_n_sample, scaled_forward;
 } m5_nar_cfg;
 
 /*
@@ -130,7 +137,9 @@ typedef struct {
  * c_codes  [sum c_codes_len][8]  reference codes (prompt)
  * x_l0     [sum x_len]           AR L0 codes (the `_x[...,0]` column, inference.py:282)
  * x_init   [sum x_len][8]        optional initial randint draw (diffuser.py:409) for parity, else NULL (Philox)
- * noise    [T][2][sum S][8][K]   optional uniforms for the two rand_like draws per step (parity, tiny cases), else NULL
+ * noise    [n_steps][2][sum S][8][K]  optional uniforms for the rand_like draws (parity, tiny cases), else NULL; n_steps =
+ *          T without jumps, else len(get_schedule) - 1; a reverse step uses draw 0 (unknown sample) and draw 1 (known
+ *          re-noise), a forward step draw 0
  * out_codes[sum x_len][8]        result after the deep-clone crop (diffuser.py:471)
  */
 int m5_nar_infer(m5_ctx* ctx, int32_t B, const int32_t* c_text, const int32_t* c_text_len, const int32_t* c_codes,

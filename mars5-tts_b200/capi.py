@@ -33,13 +33,13 @@ class ArCfg(C.Structure):
     _fields_ = [("temperature", C.c_float), ("top_k", C.c_int32), ("top_p", C.c_float),
                 ("alpha_frequency", C.c_float), ("alpha_presence", C.c_float), ("penalty_window", C.c_int32),
                 ("eos_penalty_decay", C.c_float), ("eos_penalty_factor", C.c_float), ("max_len", C.c_int32),
-                ("eos_id", C.c_int32), ("force_len", C.c_int32), ("sync_every", C.c_int32)]
+                ("eos_id", C.c_int32), ("force_len", C.c_int32), ("sync_every", C.c_int32), ("typical_p", C.c_float)]
 
 
 class NarCfg(C.Structure):
     _fields_ = [("T", C.c_int32), ("x0_temp", C.c_float), ("guidance_w", C.c_float),
                 ("q0_override_steps", C.c_int32), ("deep_clone", C.c_int32), ("precise", C.c_int32),
-                ("schedule", C.c_void_p)]
+                ("schedule", C.c_void_p), ("jump_len", C.c_int32), ("jump_n_sample", C.c_int32), ("scaled_forward", C.c_int32)]
 
 
 _P = C.c_void_p

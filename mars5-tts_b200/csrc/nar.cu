@@ -11,6 +11,7 @@
 // the model (mask m[...,0]=True, diffuser.py:419-420), so its head is skipped in the loop.
 #include <math.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "layers.h"
@@ -496,18 +497,49 @@ int m5_nar_infer(m5_ctx* ctx, int32_t B, const int32_t* c_text, const int32_t* c
   } else {
     make_schedule(T, sch);
   }
-  // RePaint schedule with jump_len = jump_n_sample = 1 is simply T-1 ... 0 (diffuser.py:318-333, inference.py:291)
-  for (int step = 0; step < T; ++step) {
-    const int t = T - 1 - step;
-    M5_TRY(nar_trunk(ctx, w, p, d_x, t, precise, nb));
+  // RePaint schedule (get_schedule, diffuser.py:318-333); with jump_len = jump_n_sample = 1 it is simply T-1 ... 0
+  const int jl = std::max(1, cfg->jump_len), jn = std::max(1, cfg->jump_n_sample);
+  if ((jl > 1 || jn > 1) && cfg->scaled_forward)
+    return ctx->fail(M5_ERR_ARG, "RePaint jumps with enable_kevin_scaled_inference: the reference's q_pred_one_timestep_scaled "
+                                 "(diffuser.py:136-159) raises for every sequence length != 8; pass scaled_forward = 0");
+  std::vector<int> times;
+  {
+    std::vector<int> jumps(T + 1, 0);
+    for (int j = 0; j < T - jl; j += jl) jumps[j] = jn - 1;
+    int t = T;
+    while (t >= 1) {
+      t -= 1;
+      times.push_back(t);
+      if (jumps[t] > 0) {
+        jumps[t] -= 1;
+        for (int i = 0; i < jl; ++i) { t += 1; times.push_back(t); }
+      }
+    }
+    times.push_back(-1);
+  }
+  for (size_t step = 0; step + 1 < times.size(); ++step) {
+    const int t = times[step], t_cur = times[step + 1];
     const float* u0 = nullptr; const float* u1 = nullptr;
     if (noise) {
       const size_t per = (size_t)Rx * Q * K;
       if (mem == M5_MEM_HOST) {
-        M5_CUDA(cudaMemcpyAsync(d_noise, noise + (size_t)step * 2 * per, 2 * per * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        M5_CUDA(cudaMemcpyAsync(d_noise, noise + step * 2 * per, 2 * per * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         u0 = d_noise; u1 = d_noise + per;
-      } else { u0 = noise + (size_t)step * 2 * per; u1 = u0 + per; }
+      } else { u0 = noise + step * 2 * per; u1 = u0 + per; }
     }
+    RenoiseCall rc;
+    rc.R = (int)Rx; rc.Q = Q; rc.K = K; rc.x = d_x; rc.x_q0 = d_q0; rc.t = t;
+    rc.q0_override = (cfg->q0_override_steps < t) ? 1 : 0;  // retain_quant0 (diffuser.py:467-468)
+    rc.seed = seed; rc.row_utt = p.x_utt; rc.row_pos = p.x_pos;
+    if (t_cur > t) {
+      // forward step x_t -> x_{t+1} ~ q(x_{t+1} | x_t) for EVERY entry (forward_diffusion, diffuser.py:336-342,462-465)
+      rc.forward = 1; rc.x_known = d_x; rc.known = d_m; rc.u = u0;
+      rc.log_cum_t = sch.log_alpha[t]; rc.log_1m_cum_t = sch.log_1m_alpha[t];
+      if (nar_renoise(rc, ctx->stream) != M5_OK) return ctx->fail(M5_ERR_CUDA, "nar_renoise(forward) failed");
+      ctx->launches++;
+      continue;
+    }
+    M5_TRY(nar_trunk(ctx, w, p, d_x, t, precise, nb));
     for (int q = 1; q < Q; ++q) {  // codebook 0 is always known
       M5_TRY(nar_head(ctx, w, p, q, precise, nb));
       PosteriorCall pc;
@@ -520,11 +552,8 @@ int m5_nar_infer(m5_ctx* ctx, int32_t B, const int32_t* c_text, const int32_t* c
       if (nar_posterior(pc, ctx->stream) != M5_OK) return ctx->fail(M5_ERR_CUDA, "nar_posterior failed");
       ctx->launches++;
     }
-    RenoiseCall rc;
-    rc.R = (int)Rx; rc.Q = Q; rc.K = K; rc.x_known = d_xk; rc.known = d_m; rc.x = d_x; rc.x_q0 = d_q0;
-    rc.log_cum_t = sch.log_cum[t]; rc.log_1m_cum_t = sch.log_1m_cum[t]; rc.t = t;
-    rc.q0_override = (cfg->q0_override_steps < t) ? 1 : 0;  // retain_quant0 (diffuser.py:467-468)
-    rc.u = u1; rc.seed = seed; rc.row_utt = p.x_utt; rc.row_pos = p.x_pos;
+    rc.x_known = d_xk; rc.known = d_m; rc.u = u1;
+    rc.log_cum_t = sch.log_cum[t]; rc.log_1m_cum_t = sch.log_1m_cum[t];
     if (nar_renoise(rc, ctx->stream) != M5_OK) return ctx->fail(M5_ERR_CUDA, "nar_renoise failed");
     ctx->launches++;
   }

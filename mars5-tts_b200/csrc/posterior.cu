@@ -175,11 +175,11 @@ __global__ void __launch_bounds__(256) nar_renoise_kernel(RenoiseCall p, float l
   const int lane = threadIdx.x & 31;
   if (item >= p.R * p.Q) return;
   const int row = item / p.Q, q = item - row * p.Q;
-  const bool known = p.known[item] != 0;
+  const bool known = p.forward || p.known[item] != 0;
   int result;
   if (!known) {
     result = p.x[item];
-  } else if (p.t == 0) {
+  } else if (p.t == 0 && !p.forward) {
     result = p.x_known[item];
   } else {
     const int xk = p.x_known[item];
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) nar_renoise_kernel(RenoiseCall p, float l
     const float v_diff = log_add_exp(log_eps + p.log_cum_t, c1);
     const uint64_t utt = p.row_utt ? (uint64_t)p.row_utt[row] : 0ull;
     const uint32_t pos = p.row_pos ? (uint32_t)p.row_pos[row] : (uint32_t)row;
-    const uint32_t tag = ((uint32_t)p.t << 8) | (1u << 4) | (uint32_t)q;
+    const uint32_t tag = ((uint32_t)p.t << 8) | ((p.forward ? 2u : 1u) << 4) | (uint32_t)q;
     const float* un = p.u ? p.u + (size_t)item * K : nullptr;
     float best = -INFINITY;
     int best_k = 0x7FFFFFFF;

@@ -8,7 +8,10 @@
 //   4. z /= temperature
 //   5. top-k: exact k-th largest by an 8-bit radix select; everything < kth is removed, ties kept (samplers.py:70-74)
 //   6. top-p over the descending-sorted survivors with the "keep the first token over the threshold" shift
-//      (samplers.py:76-91); typical-p is the identity at mass 1.0 (samplers.py:100)
+//      (samplers.py:76-91)
+//   6b. typical-p (samplers.py:96-122; identity for mass > 0.999): over the tokens still alive, score_i = |-log p_i - H|;
+//      the tokens are ranked by score, the score at the first rank whose cumulative probability reaches `mass` is the
+//      threshold, every token with a larger score is removed (ties at the threshold survive)
 //   7. log_softmax, p = exp(logp), sample argmax_i p_i / e_i with e_i ~ Exp(1) -- exactly torch.multinomial's n=1 path
 //      (ar_generate.py:102-118).  e_i comes from the caller's noise tensor (parity) or Philox4x32-10 keyed by
 //      (seed, utterance id, step, i) (production).
@@ -194,6 +197,70 @@ __global__ void __launch_bounds__(SP_THREADS) ar_sample_kernel(SampleCall p) {
   }
   __syncthreads();
   const int keep = s_ncut;
+  // ---- step 6b: typical-p over the `keep` survivors (ar_generate.py:93)
+  if (p.cfg.typical_p > 0.f && p.cfg.typical_p <= 0.999f && keep > 0) {
+    float* ts = reinterpret_cast<float*>(si + p.cap);   // [cap] scores, later sorted ascending
+    float* tp = ts + p.cap;                              // [cap] probabilities carried along
+    // log_softmax over the survivors, entropy
+    part = 0.f;
+    for (int i = tid; i < keep; i += SP_THREADS) part += expf(sv[i] - vmax);
+    part = warp_sum(part);
+    if ((tid & 31) == 0) s_red[tid >> 5] = part;
+    __syncthreads();
+    float ssum = 0.f;
+    for (int w = 0; w < SP_THREADS / 32; ++w) ssum += s_red[w];
+    const float lse_t = logf(ssum);
+    __syncthreads();
+    float ent = 0.f;
+    for (int i = tid; i < keep; i += SP_THREADS) {
+      const float nl = (sv[i] - vmax) - lse_t;
+      ent -= nl * expf(nl);
+    }
+    ent = warp_sum(ent);
+    if ((tid & 31) == 0) s_red[tid >> 5] = ent;
+    __syncthreads();
+    float H = 0.f;
+    for (int w = 0; w < SP_THREADS / 32; ++w) H += s_red[w];
+    __syncthreads();
+    int kp2 = 1;
+    while (kp2 < keep) kp2 <<= 1;
+    for (int i = tid; i < kp2; i += SP_THREADS) {
+      if (i < keep) {
+        const float nl = (sv[i] - vmax) - lse_t;
+        ts[i] = fabsf(-nl - H);
+        tp[i] = expf(nl);
+      } else { ts[i] = INFINITY; tp[i] = 0.f; }
+    }
+    __syncthreads();
+    for (int size = 2; size <= kp2; size <<= 1) {      // bitonic sort, ascending by score
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = tid; i < kp2 / 2; i += SP_THREADS) {
+          const int lo = (i / stride) * stride * 2 + (i % stride);
+          const int hi = lo + stride;
+          const bool asc = ((lo & size) == 0);
+          const float a = ts[lo], c = ts[hi];
+          if ((a > c) == asc) { ts[lo] = c; ts[hi] = a; const float q = tp[lo]; tp[lo] = tp[hi]; tp[hi] = q; }
+        }
+        __syncthreads();
+      }
+    }
+    if (tid == 0) {
+      float cum = 0.f;
+      int last = 0;
+      for (int i = 0; i < keep; ++i) {   // last_ind = #(cumulative_probs < mass)
+        cum += tp[i];
+        if (cum < p.cfg.typical_p) last = i + 1;
+      }
+      s_bcast[0] = ts[min(last, keep - 1)];
+    }
+    __syncthreads();
+    const float thr = s_bcast[0];
+    for (int i = tid; i < keep; i += SP_THREADS) {
+      const float nl = (sv[i] - vmax) - lse_t;
+      if (fabsf(-nl - H) > thr) sv[i] = NEG;   // removed: exp(-inf) = 0 in the final softmax, never sampled
+    }
+    __syncthreads();
+  }
   // ---- step 7: log_softmax over the kept set, sample argmax p_i / e_i
   part = 0.f;
   for (int i = tid; i < keep; i += SP_THREADS) part += expf(sv[i] - vmax);
@@ -258,7 +325,7 @@ __global__ void __launch_bounds__(SP_THREADS) ar_sample_kernel(SampleCall p) {
   }
 }
 
-size_t sample_smem_bytes(int V, int cap) { return (size_t)((V + 3) & ~3) * 4 + (size_t)cap * 8; }
+size_t sample_smem_bytes(int V, int cap) { return (size_t)((V + 3) & ~3) * 4 + (size_t)cap * 16; }  // z | sv | si | typical-p scores, probs
 
 int sample_cap(int V, int top_k) {
   int want = top_k > 0 ? min(V, 2 * top_k + 64) : V;
@@ -271,12 +338,10 @@ int ar_sample(SampleCall& c, cudaStream_t stream) {
   if (c.B <= 0) return M5_OK;
   c.cap = sample_cap(c.V, c.cfg.top_k);
   const size_t smem = sample_smem_bytes(c.V, c.cap);
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(ar_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return M5_ERR_CUDA;
-    configured = smem;
-  }
+  // the opt-in shared-memory size is a per-device, per-function attribute: set on every launch (no process-wide cache)
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(ar_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return M5_ERR_CUDA;
   return launch_k(ar_sample_kernel, dim3(c.B), dim3(SP_THREADS), smem, stream, c) == cudaSuccess ? M5_OK : M5_ERR_CUDA;
 }
 

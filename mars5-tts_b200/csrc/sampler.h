@@ -74,6 +74,10 @@ struct RenoiseCall {
   uint64_t seed = 0;
   const int64_t* row_utt = nullptr;
   const int* row_pos = nullptr;
+  // forward = 1: RePaint forward step x_t -> x_{t+1} (forward_diffusion, diffuser.py:336-342): every entry is re-drawn
+  // from q_pred_one_timestep of ITSELF (x_known aliases x, `known` is ignored, log_cum_t / log_1m_cum_t carry
+  // log_alpha[t] / log_1_min_alpha[t], no t == 0 shortcut)
+  int forward = 0;
 };
 int nar_renoise(const RenoiseCall& c, cudaStream_t stream);
 

@@ -122,6 +122,7 @@ class Engine:
         c.alpha_frequency, c.alpha_presence, c.penalty_window = icfg.freq_penalty, icfg.presence_penalty, icfg.rep_penalty_window
         c.eos_penalty_decay, c.eos_penalty_factor = icfg.eos_penalty_decay, icfg.eos_penalty_factor
         c.max_len, c.eos_id, c.force_len, c.sync_every = max_len, eos_id, force_len, sync_every
+        c.typical_p = icfg.typical_p
         return c
 
     def ar_generate_packed(self, ids, plen, codes, slen, nph, ar_cfg, noise=None, seed=0, utt=None, dump_steps=0):
@@ -171,13 +172,14 @@ class Engine:
             self._sched_cache[T] = np.ascontiguousarray(weights.diffusion_schedule(T).numpy())
         return self._sched_cache[T]
 
-    def make_nar_cfg(self, icfg: InferenceConfig, T=200, precise=capi.NUM_MIXED):
+    def make_nar_cfg(self, icfg: InferenceConfig, T=200, precise=capi.NUM_MIXED, jump_len=1, jump_n_sample=1, scaled_forward=False):
         """precise: NAR numerics (capi.NUM_FAST / NUM_PRECISE / NUM_MIXED; True == NUM_PRECISE).  The default, mixed, is the
         cheapest setting whose logits stay within 1e-3 max-abs of the fp32 reference."""
         c = capi.NarCfg()
         c.T, c.x0_temp, c.guidance_w = T, icfg.x_0_temp, icfg.nar_guidance_w
         c.q0_override_steps, c.deep_clone, c.precise = icfg.q0_override_steps, int(icfg.deep_clone), int(precise)
         c.schedule = self.schedule(T).ctypes.data
+        c.jump_len, c.jump_n_sample, c.scaled_forward = int(jump_len), int(jump_n_sample), int(scaled_forward)
         return c
 
     def nar_infer_packed(self, text, tlen, codes, clen, l0, xlen, nar_cfg, x_init=None, noise=None, seed=0, utt=None):

@@ -156,8 +156,26 @@ def warp_logits(logits, prev_ids, scfg, text_vocab, eos_idx, n_phones_gen):
         rm[1:] = rm[:-1].clone()
         rm[0] = False
         z[si[rm]] = float("-inf")
+    tp = scfg.get("typical_p", 1.0)
+    if tp <= 0.999:  # apply_typical_p (samplers.py:96-122), applied after top-k / top-p (ar_generate.py:93)
+        z = typical_p_filter(z, tp)
     z[: text_vocab - 1] = float("-inf")
     return z.log_softmax(-1)
+
+
+def typical_p_filter(logits, mass):
+    """apply_typical_p (samplers.py:96-122) for one row of (already filtered) logits."""
+    normalized = logits.log_softmax(-1)
+    p = normalized.exp()
+    ent = -(normalized * p).nansum(-1, keepdim=True)
+    shifted = ((-normalized) - ent).abs()
+    sorted_scores, sorted_idx = torch.sort(shifted, descending=False)
+    cum = logits[sorted_idx].softmax(-1).cumsum(-1)
+    last = int((cum < mass).sum())
+    thr = sorted_scores[min(last, len(sorted_scores) - 1)]
+    out = logits.clone()
+    out[shifted > thr] = float("-inf")
+    return out
 
 
 def sample_token(logprobs, exp_noise):

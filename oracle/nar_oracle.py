@@ -151,9 +151,33 @@ def reverse_step(tabs, cond, uncond, x, x_known, m, t, guidance_w, temp, u_unkno
     return x_kn * m.long() + x_unknown * (1 - m.long()), logp
 
 
+def get_schedule(t_T, jump_len=10, jump_n_sample=10):
+    """RePaint resampling schedule (diffuser.py:318-333)."""
+    jumps = {j: jump_n_sample - 1 for j in range(0, t_T - jump_len, jump_len)}
+    t, ts = t_T, []
+    while t >= 1:
+        t -= 1
+        ts.append(t)
+        if jumps.get(t, 0) > 0:
+            jumps[t] -= 1
+            for _ in range(jump_len):
+                t += 1
+                ts.append(t)
+    ts.append(-1)
+    return ts
+
+
+def forward_step(tabs, x, t, u, K):
+    """forward_diffusion with c=None (diffuser.py:336-342): x_{t+1} ~ q_pred_one_timestep(onehot(x_t), t), every entry."""
+    la, l1ma, _, _ = tabs
+    return gumbel_argmax(log_add_exp(log_onehot(x, K) + la[t], l1ma[t] - np.log(K)), u)
+
+
 def nar_infer(sd, cfg, c_text, c_codes, x_l0, ncfg, x_init, noise):
-    """perform_simple_inference (diffuser.py:398-472) for one utterance with jump_len = jump_n_sample = 1.
-    x_init: (N, Q) initial randint draw; noise: (T, 2, S, Q, K) uniforms (draw 0 unknown sample, draw 1 known re-noise).
+    """perform_simple_inference (diffuser.py:398-472) for one utterance.
+    x_init: (N, Q) initial randint draw; noise: (n_steps, 2, S, Q, K) uniforms, n_steps = len(get_schedule) - 1 (= T
+    without jumps): a reverse step uses draw 0 (unknown sample) and draw 1 (known re-noise), a forward step draw 0.
+    ncfg may carry jump_len / jump_n_sample (RePaint; unscaled forward diffusion, enable_kevin_scaled_inference=False).
     Returns codes (N, Q) after the deep-clone crop."""
     K, Q, T = cfg["n_classes"], cfg["n_quant"], ncfg["T"]
     tabs = diffusion_tables(T)
@@ -171,11 +195,15 @@ def nar_infer(sd, cfg, c_text, c_codes, x_l0, ncfg, x_init, noise):
         m = torch.cat([torch.ones_like(c_codes).bool(), m], dim=0)
         x_q0 = torch.cat([c_codes[:, 0], x_q0], dim=0)
         offset = c_codes.shape[0]
-    for step, t in enumerate(range(T - 1, -1, -1)):
-        cond = nar_forward(sd, cfg, c_text, c_codes, x, t, drop_cond=False)
-        uncond = nar_forward(sd, cfg, c_text, c_codes, x, t, drop_cond=True) if ncfg["guidance_w"] != 1 else None
-        x, _ = reverse_step(tabs, cond, uncond, x, x_known, m, t, ncfg["guidance_w"], ncfg["x0_temp"], noise[step, 0],
-                            noise[step, 1], K)
+    times = get_schedule(T, ncfg.get("jump_len", 1), ncfg.get("jump_n_sample", 1))
+    for step, (t, t_cur) in enumerate(zip(times[:-1], times[1:])):
+        if t_cur < t:
+            cond = nar_forward(sd, cfg, c_text, c_codes, x, t, drop_cond=False)
+            uncond = nar_forward(sd, cfg, c_text, c_codes, x, t, drop_cond=True) if ncfg["guidance_w"] != 1 else None
+            x, _ = reverse_step(tabs, cond, uncond, x, x_known, m, t, ncfg["guidance_w"], ncfg["x0_temp"], noise[step, 0],
+                                noise[step, 1], K)
+        else:
+            x = forward_step(tabs, x, t, noise[step, 0], K)
         if ncfg["q0_override_steps"] < t:
             x[:, 0] = x_q0
     return x[offset:]

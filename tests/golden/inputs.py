@@ -64,3 +64,37 @@ def trim_cases():
     cases.append(("full_utterance_length", burst(1499 * 320, [(30000, 420000, 0.25)], 3e-4)))
     cases.append(("shortest_legal", burst(1025, [(100, 900, 0.2)], 1e-4)))
     return cases
+
+
+def make_extra_inputs():
+    """Replays make_golden_extra.py's draws (generator seed 4321, same order): typical-p logits and the RePaint case.
+    The (n_draws, S, 8, K) uniforms are expanded into the engine's (n_steps, 2, S, 8, K) layout (reverse step: draw 0 =
+    unknown sample, draw 1 = known re-noise; forward step: draw 0)."""
+    import numpy as np
+    n_text = 258
+    V = n_text + 1025
+    g = torch.Generator().manual_seed(4321)
+    d = {}
+    lg = torch.randn(4, V, generator=g) * 3
+    lg[:, : n_text - 1] = float("-inf")
+    d["typ_logits"] = lg
+    Pf, Tc, N, T = 12, 11, 7, 6
+    d["rp_c_text"] = torch.randint(0, n_text, (Tc,), generator=g)
+    d["rp_c_codes"] = torch.randint(0, 1024, (Pf, 8), generator=g)
+    d["rp_x_l0"] = torch.randint(0, 1024, (N,), generator=g)
+    d["rp_x_init"] = torch.randint(0, 1025, (N, 8), generator=g)
+    times = [5, 4, 3, 2, 3, 4, 3, 2, 1, 0, 1, 2, 1, 0, -1]   # get_schedule(6, jump_len=2, jump_n_sample=2)
+    n_draws = sum(2 if (b < a and a > 0) else 1 for a, b in zip(times[:-1], times[1:]))
+    for tag, S in (("deep", N + Pf), ("shallow", N)):
+        u = torch.rand(n_draws, S, 8, 1025, generator=g)
+        d[f"chk_rp_{tag}_u"] = float(u.double().sum())
+        full = torch.full((len(times) - 1, 2, S, 8, 1025), 0.5)
+        i = 0
+        for s, (a, b) in enumerate(zip(times[:-1], times[1:])):
+            full[s, 0] = u[i]; i += 1
+            if b < a and a > 0:
+                full[s, 1] = u[i]; i += 1
+        assert i == n_draws
+        d[f"rp_{tag}_u"] = full
+    d["rp_times"], d["rp_T"], d["n_text"], d["V"] = times, T, n_text, V
+    return d

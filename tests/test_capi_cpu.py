@@ -30,13 +30,20 @@ def test_ctypes_table_matches_header():
     assert sorted(capi.exported_symbols()) == _header_symbols()
 
 
-def test_struct_sizes_match_header_layout():
+def test_struct_sizes_match_header_layout(tmp_path):
+    """sizeof / offsetof of every struct of the header as gcc lays them out == the ctypes mirrors in capi.py."""
     import ctypes as C
-    # m5_model_cfg: 8 int32 + 2 float + 9 int32 + 5 float + 9 int32 ; m5_ar_cfg: 12 x 4 bytes ; m5_nar_cfg: 6 x 4 + pointer
+    src = tmp_path / "sz.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "mars5_b200.h"\n'
+        'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(m5_model_cfg), sizeof(m5_ar_cfg), sizeof(m5_nar_cfg), '
+        'sizeof(m5_tensor), offsetof(m5_ar_cfg, typical_p), offsetof(m5_nar_cfg, schedule), offsetof(m5_nar_cfg, jump_len)); return 0; }\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [C.sizeof(capi.ModelCfg), C.sizeof(capi.ArCfg), C.sizeof(capi.NarCfg), C.sizeof(capi.Tensor),
+                   capi.ArCfg.typical_p.offset, capi.NarCfg.schedule.offset, capi.NarCfg.jump_len.offset], got
     assert C.sizeof(capi.ModelCfg) == 4 * (8 + 2 + 9 + 5 + 9)
-    assert C.sizeof(capi.ArCfg) == 48
-    assert C.sizeof(capi.NarCfg) == 32
-    assert C.sizeof(capi.Tensor) == 32
 
 
 def test_built_for_sm100a_with_tcgen05_and_tma():

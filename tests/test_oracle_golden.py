@@ -117,3 +117,46 @@ def test_nar_loop_codes(env, deep):
     codes = nar_oracle.nar_infer(nar_sd, cfg, inp["nar_c_text"], inp["nar_c_codes"], inp["nar_loop_x_l0"], ncfg,
                                  inp["nar_loop_x_init"], inp[f"nar_loop_{tag}_u"])
     np.testing.assert_array_equal(codes.numpy(), GOLD[f"nar_loop_{tag}_codes"])
+
+
+# ------------------------------------------------------------------------------------------------ round-2 fixtures
+EXTRA = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_extra.npz"))
+
+
+@pytest.fixture(scope="module")
+def extra():
+    from tests.golden.inputs import make_extra_inputs
+    return make_extra_inputs()
+
+
+def test_extra_inputs_match_fixture(extra):
+    for tag in ("deep", "shallow"):
+        assert abs(extra[f"chk_rp_{tag}_u"] - float(EXTRA[f"chk_rp_{tag}_u"])) < 1e-6 * abs(float(EXTRA[f"chk_rp_{tag}_u"]))
+    np.testing.assert_array_equal(extra["typ_logits"].numpy(), EXTRA["typ_logits"])
+    assert nar_oracle.get_schedule(6, 2, 2) == EXTRA["rp_times"].tolist() == extra["rp_times"]
+    assert nar_oracle.get_schedule(200, 1, 1) == list(range(199, -2, -1))
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_typical_p_matches_reference(extra, name):
+    """apply_typical_p chained after top-k / top-p exactly as ar_generate.py:88-97 does (samplers.py:96-122)."""
+    temp, k, p, mass = EXTRA[f"typ_{name}_cfg"].tolist()
+    sc = dict(SCFG, temperature=temp, top_k=int(k), top_p=p, typical_p=mass, alpha_frequency=0, alpha_presence=0)
+    for b in range(4):
+        lp = ar_oracle.warp_logits(extra["typ_logits"][b], [], sc, extra["n_text"], -1, None)
+        ref = torch.from_numpy(EXTRA[f"typ_{name}"][b])
+        assert torch.equal(torch.isfinite(lp), torch.isfinite(ref)), (name, b, int(torch.isfinite(lp).sum()), int(torch.isfinite(ref).sum()))
+        fin = torch.isfinite(ref)
+        assert 0 < int(fin.sum()) < int(torch.isfinite(extra["typ_logits"][b]).sum())
+        assert (lp[fin] - ref[fin].log_softmax(-1)).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("deep", [True, False])
+def test_nar_infer_repaint_jumps_code_exact(env, extra, deep):
+    """perform_simple_inference with get_schedule(T, jump_len=2, jump_n_sample=2) and the unscaled forward step."""
+    _, _, nar_sd, cfg = env
+    tag = "deep" if deep else "shallow"
+    codes = nar_oracle.nar_infer(nar_sd, cfg, extra["rp_c_text"], extra["rp_c_codes"], extra["rp_x_l0"],
+                                 dict(T=extra["rp_T"], deep_clone=deep, guidance_w=3, x0_temp=0.7, q0_override_steps=2, jump_len=2,
+                                      jump_n_sample=2), extra["rp_x_init"], extra[f"rp_{tag}_u"])
+    np.testing.assert_array_equal(codes.numpy(), EXTRA[f"rp_{tag}_codes"])

@@ -255,3 +255,71 @@ def test_vocode_matches_oracle(tiny):
         rms = float(np.sqrt(np.mean((w - ref) ** 2)))
         scale = float(np.sqrt(np.mean(ref ** 2)))
         assert rms < 1e-4 * max(1.0, scale), (len(c), rms, scale)
+
+
+# ------------------------------------------------------------------------------------------------ round-2 boundary rows
+EXTRA = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_extra.npz"))
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_sampler_typical_p_matches_reference(tiny, name):
+    """InferenceConfig.typical_p < 1 (samplers.py:96-122): the surviving set and the log-probs of the fused sampler against
+    the unmodified reference's apply_typical_p chained after top-k / top-p (fixture), and the sampled id against the oracle."""
+    from tests.golden.inputs import make_extra_inputs
+    inp, _, _, _, eng, cfg = tiny
+    ex = make_extra_inputs()
+    temp, k, p, mass = EXTRA[f"typ_{name}_cfg"].tolist()
+    V, n_text = inp["V"], inp["n_text"]
+    B = 4
+    g = torch.Generator().manual_seed(91)
+    noise = torch.empty(B, 1, V).exponential_(1, generator=g)
+    ic = InferenceConfig(temperature=temp, top_k=int(k), top_p=p, typical_p=mass, freq_penalty=0, presence_penalty=0)
+    acfg = eng.make_ar_cfg(ic, 2000, -1)
+    d = lambda t: t.to(DEV).contiguous()
+    lg_d, nz_d = d(ex["typ_logits"]), d(noise)
+    hist = torch.zeros(B, 4, dtype=torch.int32, device=DEV)
+    ng = torch.zeros(B, dtype=torch.int32, device=DEV)
+    tok = torch.zeros(B, dtype=torch.int32, device=DEV)
+    lp = torch.zeros(B, V, device=DEV)
+    rc = eng.lib.m5_dbg_sample(eng.ctx, ptr(lg_d), B, V, C.byref(acfg), n_text, ptr(hist), 4, ptr(ng), None, ptr(nz_d), 0, ptr(tok), ptr(lp))
+    capi.check(eng.ctx, rc, "sample")
+    _sync(eng)
+    for b in range(B):
+        ref = torch.from_numpy(EXTRA[f"typ_{name}"][b])
+        got = lp[b].cpu()
+        assert torch.equal(torch.isfinite(got), torch.isfinite(ref)), (name, b)
+        fin = torch.isfinite(ref)
+        ref_lp = ref[fin].log_softmax(-1)
+        assert (got[fin] - ref_lp).abs().max().item() < 2e-5
+        full = torch.full((V,), float("-inf")); full[fin] = ref_lp
+        assert int(tok[b]) == ar_oracle.sample_token(full, noise[b, 0])
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("deep", [True, False])
+def test_nar_infer_repaint_jumps_match_reference(tiny, deep, mode):
+    """RePaint resampling (jump_len = jump_n_sample = 2, unscaled forward diffusion): codes bit-exact against the
+    unmodified reference's perform_simple_inference (tests/golden/make_golden_extra.py)."""
+    from tests.golden.inputs import make_extra_inputs
+    inp, _, _, _, eng, _ = tiny
+    ex = make_extra_inputs()
+    tag = "deep" if deep else "shallow"
+    ic = InferenceConfig(deep_clone=deep, q0_override_steps=2)
+    ncfg = eng.make_nar_cfg(ic, T=ex["rp_T"], precise=mode, jump_len=2, jump_n_sample=2)
+    codes = eng.nar_infer([ex["rp_c_text"].numpy()], [ex["rp_c_codes"].numpy()], [ex["rp_x_l0"].numpy()], ncfg,
+                          x_init=[ex["rp_x_init"].numpy()], noise=ex[f"rp_{tag}_u"].numpy())[0]
+    np.testing.assert_array_equal(codes, EXTRA[f"rp_{tag}_codes"])
+
+
+def test_nar_infer_scaled_forward_is_rejected(tiny):
+    inp, _, _, _, eng, _ = tiny
+    ncfg = eng.make_nar_cfg(InferenceConfig(), T=6, jump_len=2, jump_n_sample=2, scaled_forward=True)
+    with pytest.raises(capi.M5Error, match="q_pred_one_timestep_scaled"):
+        eng.nar_infer([inp["nar_c_text"].numpy()], [inp["nar_c_codes"].numpy()], [inp["nar_loop_x_l0"].numpy()], ncfg)
+
+
+def test_ar_generate_rejects_more_than_32_rows(tiny):
+    inp, _, _, _, eng, _ = tiny
+    acfg = eng.make_ar_cfg(InferenceConfig(), 40, inp["eos"])
+    with pytest.raises(capi.M5Error, match="at most 32"):
+        eng.ar_generate([inp["ar_prompt"].tolist()] * 33, [inp["ar_spk"].numpy()] * 33, [7] * 33, acfg)
