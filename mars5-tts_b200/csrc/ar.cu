@@ -124,6 +124,9 @@ static int ar_build_plan(m5_ctx* ctx, Arena& ar, ArPlan& p, int B, const int* pr
   std::vector<int> code_row, spos, sstart, slen, sfirst, tok, pos, rseq, qstart, qlen, last;
   int r = 0, co = 0, mx = 0;
   for (int b = 0; b < B; ++b) {
+    if (1 + p.Pf[b] > ctx->cfg.max_pos || p.Pf[b] < 0 || p.P[b] <= 0)
+      return ctx->fail(M5_ERR_ARG, "utterance " + std::to_string(b) + ": speaker reference of " + std::to_string(p.Pf[b]) +
+                                       " frames exceeds m5_model_cfg.max_pos = " + std::to_string(ctx->cfg.max_pos) + " (or empty prompt)");
     p.c_off[b] = co;
     sstart.push_back(r); slen.push_back(1 + p.Pf[b]); sfirst.push_back(r);
     code_row.push_back(-1); spos.push_back(0);
@@ -359,6 +362,11 @@ int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int3
   const m5_model_cfg& c = ctx->cfg;
   const int D = c.ar_dim, V = c.ar_vocab, Q = c.n_quant, F = c.ar_hidden, L = c.ar_layers;
   const int max_len = cfg->max_len;
+  // The reference attends through a 3000-position sliding window (ar_generate.py:57, nn_future.py:381-392); the cache here
+  // never rotates, which is identical as long as spk slot + max_len tokens fit the window.
+  if (max_len + 1 > 3000)
+    return ctx->fail(M5_ERR_ARG, "max_len " + std::to_string(max_len) + " exceeds the reference's 3000-position sliding window "
+                                 "(ar_generate.py:57): longer generations are not implemented");
   size_t n_ids = 0, n_codes = 0; int maxP = 0, minP = 1 << 30;
   for (int b = 0; b < B; ++b) {
     n_ids += prompt_len[b]; n_codes += spk_len[b];
@@ -424,6 +432,10 @@ int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int3
     if (!dp.layers || !dp.ssq || !dp.attn_part || !dp.scratch || !dp.counters || !dp.gbar)
       return ctx->fail(M5_ERR_NOMEM, "arena too small (fused decode buffers)");
     cudaMemsetAsync(dp.counters, 0, (ar_decode_max_tiles(dp) + 1) * sizeof(int), ctx->stream);
+    if (getenv("M5_AR_PROFILE")) {   // per-phase timeline of CTA 0 of the LAST decode step, printed to stderr after the loop
+      dp.prof = reinterpret_cast<unsigned long long*>(ar.get<double>((size_t)2 * (5 * L + 2)));
+      if (dp.prof) cudaMemsetAsync(dp.prof, 0, sizeof(double) * 2 * (5 * L + 2), ctx->stream);
+    }
   }
   const float* d_noise = noise;
   if (noise && mem == M5_MEM_HOST) {
@@ -504,6 +516,25 @@ int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int3
     }
   }
   if (pe) prof_end(ctx, pe, 2, 0.0, 0.0, steps_run);
+  if (dp.prof && steps_run > 0 && !legacy_decode) {
+    std::vector<unsigned long long> ts((size_t)2 * (5 * L + 2));
+    cudaMemcpyAsync(ts.data(), dp.prof, ts.size() * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    // stamp pairs: [0] after P0, then per layer after P1 (qkv), P2 (attn), P3 (wo), P4 (w13), P5 (w2); last = end of logits
+    const char* nm[5] = {"qkv", "attn", "wo", "w13", "w2"};
+    double work[5] = {0, 0, 0, 0, 0}, wait[5] = {0, 0, 0, 0, 0};
+    for (int l = 0; l < L; ++l)
+      for (int ph = 0; ph < 5; ++ph) {
+        const size_t i = 1 + (size_t)l * 5 + ph;
+        work[ph] += (double)(ts[2 * i] - ts[2 * (i - 1) + 1]);      // barrier passed -> own work done
+        wait[ph] += (double)(ts[2 * i + 1] - ts[2 * i]);            // own work done -> barrier passed
+      }
+    fprintf(stderr, "m5 ar_decode profile (CTA 0, last step, B=%d, per layer avg us):", B);
+    for (int ph = 0; ph < 5; ++ph) fprintf(stderr, "  %s work %.1f wait %.1f", nm[ph], work[ph] / L / 1e3, wait[ph] / L / 1e3);
+    const size_t last = 1 + (size_t)5 * L;
+    fprintf(stderr, "  | P0 %.1f  logits %.1f  total %.1f us\n", (double)(ts[1] - ts[0]) / 1e3 + 0.0, (double)(ts[2 * last] - ts[2 * (last - 1) + 1]) / 1e3,
+            (double)(ts[2 * last] - ts[0]) / 1e3);
+  }
   const bool prof_rec = pe && !ctx->prof_pending.empty() && ctx->prof_pending.back().kind == 2;
   if (exec) cudaGraphExecDestroy(exec);
   if (graph) cudaGraphDestroy(graph);

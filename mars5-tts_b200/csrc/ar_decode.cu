@@ -52,8 +52,9 @@ M5_DEVINL unsigned ad_ld_acquire(const unsigned* p) {
 
 // Device-wide barrier for a co-resident grid (cooperative launch): monotonic arrival counter, zeroed by the host before
 // every launch.  `epoch` is the number of arrivals that completes the barrier this CTA is about to join.
-M5_DEVINL void grid_sync(unsigned* bar, unsigned& epoch) {
+M5_DEVINL void grid_sync(unsigned* bar, unsigned& epoch, unsigned long long* prof = nullptr) {
   __syncthreads();
+  if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[0] = global_timer_ns();
   if (threadIdx.x == 0) {
     epoch += gridDim.x;
     __threadfence();
@@ -69,6 +70,7 @@ M5_DEVINL void grid_sync(unsigned* bar, unsigned& epoch) {
       }
     }
     __threadfence();
+    if (prof && blockIdx.x == 0) prof[1] = global_timer_ns();
   }
   __syncthreads();
 }
@@ -515,7 +517,9 @@ ar_decode_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_consta
     ArGemm g = p.g_qkv; g.W = l0.wqkv;
     if ((int)blockIdx.x < g.tiles * g.ksplit) gemm_fetch(g, gemm_item(g, blockIdx.x, warp, lane), 0, wf);
   }
-  grid_sync(p.gbar, epoch);
+  unsigned long long* pf = p.prof;   // advances by 2 stamps per barrier
+  grid_sync(p.gbar, epoch, pf);
+  if (pf) pf += 2;
 
   for (int layer = 0; layer < p.n_layers; ++layer) {
     const ArLayerDev& lw = p.layers[layer];
@@ -525,34 +529,40 @@ ar_decode_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_consta
     gemm_phase<NT, X_NORM, EPI_STORE>(p, g, lw.attn_norm, p.qkv, 3 * p.D, smem, wf, (int)blockIdx.x < g.tiles * g.ksplit);
     __syncthreads();
     attn_prefetch(p, &tmap_k, &tmap_v, layer, ring, bars, ast);
-    grid_sync(p.gbar, epoch);
+    grid_sync(p.gbar, epoch, pf);
+    if (pf) pf += 2;
     // ---- P2: attention over the cache + the new token
     attn_phase(p, lw, &tmap_k, &tmap_v, layer, ring, bars, ast);
     g = p.g_wo; g.W = lw.wo;
     const bool pre_wo = (int)blockIdx.x < g.tiles * g.ksplit;
     if (pre_wo) gemm_fetch(g, gemm_item(g, blockIdx.x, warp, lane), 0, wf);
-    grid_sync(p.gbar, epoch);
+    grid_sync(p.gbar, epoch, pf);
+    if (pf) pf += 2;
     // ---- P3: x += Wo . attn
     gemm_phase<NT, X_ATTN, EPI_RESID>(p, g, nullptr, p.x, p.D, smem, wf, pre_wo);
     g = p.g_w13; g.W = lw.w13;
     const bool pre_13 = (int)blockIdx.x < g.tiles * g.ksplit;
     if (pre_13) gemm_fetch(g, gemm_item(g, blockIdx.x, warp, lane), 0, wf);
-    grid_sync(p.gbar, epoch);
+    grid_sync(p.gbar, epoch, pf);
+    if (pf) pf += 2;
     // ---- P4: g = silu(W1 . h) * (W3 . h), h = rmsnorm(x)
     gemm_phase<NT, X_NORM, EPI_SWIGLU>(p, g, lw.ffn_norm, nullptr, 0, smem, wf, pre_13);
     g = p.g_w2; g.W = lw.w2;
     const bool pre_2 = (int)blockIdx.x < g.tiles * g.ksplit;
     if (pre_2) gemm_fetch(g, gemm_item(g, blockIdx.x, warp, lane), 0, wf);
-    grid_sync(p.gbar, epoch);
+    grid_sync(p.gbar, epoch, pf);
+    if (pf) pf += 2;
     // ---- P5: x += W2 . g
     gemm_phase<NT, X_F16, EPI_RESID>(p, g, nullptr, p.x, p.D, smem, wf, pre_2);
     if (layer + 1 < p.n_layers) { g = p.g_qkv; g.W = p.layers[layer + 1].wqkv; }
     else { g = p.g_out; }
     if ((int)blockIdx.x < g.tiles * g.ksplit) gemm_fetch(g, gemm_item(g, blockIdx.x, warp, lane), 0, wf);
-    grid_sync(p.gbar, epoch);
+    grid_sync(p.gbar, epoch, pf);
+    if (pf) pf += 2;
   }
   // ---- logits = Wout . rmsnorm(x)
   gemm_phase<NT, X_NORM, EPI_STORE>(p, p.g_out, p.final_norm, p.logits, p.V, smem, wf, (int)blockIdx.x < p.g_out.tiles * p.g_out.ksplit);
+  if (pf && blockIdx.x == 0 && tid == 0) pf[0] = pf[1] = global_timer_ns();
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -626,7 +636,15 @@ int ar_decode_launch(const ArDecodeParams& p, int num_sms, cudaStream_t stream) 
   if (ad_tmap(&tk, p.kc, rows, p.D) != M5_OK || ad_tmap(&tv, p.vc, rows, p.D) != M5_OK) return M5_ERR_CUDA;
   void (*kern)(CUtensorMap, CUtensorMap, ArDecodeParams) =
       p.B <= 8 ? ar_decode_kernel<1> : (p.B <= 16 ? ar_decode_kernel<2> : ar_decode_kernel<4>);
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AD_SMEM) != cudaSuccess) return M5_ERR_CUDA;
+  static DeviceOnce once;
+  unsigned long long bit;
+  if (once.needed(bit)) {
+    if (cudaFuncSetAttribute(ar_decode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AD_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(ar_decode_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AD_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(ar_decode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AD_SMEM) != cudaSuccess)
+      return M5_ERR_CUDA;
+    once.done(bit);
+  }
   if (cudaMemsetAsync(p.gbar, 0, sizeof(unsigned), stream) != cudaSuccess) return M5_ERR_CUDA;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(num_sms); cfg.blockDim = dim3(AD_THREADS); cfg.dynamicSmemBytes = AD_SMEM; cfg.stream = stream;

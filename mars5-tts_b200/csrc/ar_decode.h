@@ -38,6 +38,7 @@ struct ArDecodeParams {
   float* scratch = nullptr;  // split-K partial tiles, ar_decode_scratch_floats()
   int* counters = nullptr;   // one ticket per row tile, zero between phases
   unsigned* gbar = nullptr;  // device-wide barrier counter
+  unsigned long long* prof = nullptr;   // optional [1 + 5 * n_layers][2] globaltimer stamps of CTA 0 (work done, barrier passed)
   ArGemm g_qkv, g_wo, g_w13, g_w2, g_out;   // g_out.W = vocabulary projection
 };
 

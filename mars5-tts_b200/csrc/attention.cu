@@ -237,10 +237,11 @@ int flash_attn(const AttnCall& c, cudaStream_t stream) {
   const bool prec = c.Qlo != nullptr;
   if (prec && (!c.Klo || !c.Vlo || !c.Olo)) return M5_ERR_ARG;
   const size_t smem = (size_t)(prec ? 10 : 5) * FA_BQ * HD * sizeof(__half);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;
+  unsigned long long bit;
+  if (once.needed(bit)) {
     cudaFuncSetAttribute(flash_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 10 * FA_BQ * HD * 2);
-    attr_set = true;
+    once.done(bit);
   }
   if (prec) flash_attn_kernel<true><<<grid, FA_THREADS, smem, stream>>>(c);
   else flash_attn_kernel<false><<<grid, FA_THREADS, smem, stream>>>(c);

@@ -415,10 +415,14 @@ int flash_attn_tc5(const AttnCall& c, cudaStream_t stream) {
   if (at_tmap(&tv, c.V, c.k_rows, cols, c.ldv, AT_BK) != M5_OK) return M5_ERR_CUDA;
   if (at_tmap(&tkl, split ? c.Klo : c.K, c.k_rows, cols, c.ldk, AT_BK) != M5_OK) return M5_ERR_CUDA;
   if (at_tmap(&tvl, split ? c.Vlo : c.V, c.k_rows, cols, c.ldv, AT_BK) != M5_OK) return M5_ERR_CUDA;
-  // the opt-in shared-memory size is a per-device attribute: set it on every launch (cheap) instead of caching a flag
-  if (cudaFuncSetAttribute(flash_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<false>::SMEM) != cudaSuccess ||
-      cudaFuncSetAttribute(flash_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<true>::SMEM) != cudaSuccess)
-    return M5_ERR_CUDA;
+  static DeviceOnce once;
+  unsigned long long bit;
+  if (once.needed(bit)) {
+    if (cudaFuncSetAttribute(flash_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<false>::SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(flash_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<true>::SMEM) != cudaSuccess)
+      return M5_ERR_CUDA;
+    once.done(bit);
+  }
   AttnTc5Params p;
   p.q_start = c.q_start; p.q_len = c.q_len; p.k_start = c.k_start; p.k_len = c.k_len; p.O = c.O; p.Olo = c.Olo; p.ldo = c.ldo;
   p.scale_log2 = c.scale * 1.4426950408889634f;

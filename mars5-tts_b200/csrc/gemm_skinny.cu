@@ -178,12 +178,13 @@ int gemm_skinny(const SkinnyCall& c, cudaStream_t stream, int num_sms) {
   if (tiles > 1024 || (size_t)tiles * ksplit > (size_t)(2 * num_sms + 64)) return M5_ERR_ARG;
   const int NT = c.B <= 8 ? 1 : (c.B <= 16 ? 2 : 4);
   const size_t smem = (size_t)(8 * NT) * (kslice * 2 + 64);
-  static bool attr_set = false;
-  if (!attr_set) {  // opt in to > 48 KB dynamic shared memory once for every instantiation
+  static DeviceOnce once;
+  unsigned long long bit;
+  if (once.needed(bit)) {  // opt in to > 48 KB dynamic shared memory once per device for every instantiation
     cudaFuncSetAttribute(gemm_skinny_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(gemm_skinny_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(gemm_skinny_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr_set = true;
+    once.done(bit);
   }
   const int grid = tiles * ksplit;
   cudaError_t e;

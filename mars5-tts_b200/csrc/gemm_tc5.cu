@@ -254,11 +254,12 @@ static int launch_kind(const GemmCall& g, cudaStream_t stream, int num_sms) {
   const int Kb = g.kwrap > 0 ? g.kwrap : g.K;  // W's stored K extent
   if (make_tmap_k64(&ta, g.A, g.M, Ka, g.lda, BLOCK_M) != M5_OK) return M5_ERR_CUDA;
   if (make_tmap_k64(&tb, g.W, g.N, Kb, g.ldw, BLOCK_N) != M5_OK) return M5_ERR_CUDA;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;   // one per template instantiation
+  unsigned long long bit;
+  if (once.needed(bit)) {
     if (cudaFuncSetAttribute(gemm_tc5_kernel<BLOCK_N, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
       return M5_ERR_CUDA;
-    attr_set = true;
+    once.done(bit);
   }
   const int m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
   const int n_tiles = (g.N + BLOCK_N - 1) / BLOCK_N;

@@ -280,11 +280,12 @@ static int launch_2cta(const GemmCall& g, cudaStream_t stream, int num_sms) {
   const int Kb = g.kwrap > 0 ? g.kwrap : g.K;
   if (make_tmap_k64(&ta, g.A, g.M, Ka, g.lda, C2_BM) != M5_OK) return M5_ERR_CUDA;
   if (make_tmap_k64(&tb, g.W, g.N, Kb, g.ldw, C2_BN / 2) != M5_OK) return M5_ERR_CUDA;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;   // one per template instantiation
+  unsigned long long bit;
+  if (once.needed(bit)) {
     if (cudaFuncSetAttribute(gemm_tc5_2cta_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_TOTAL) != cudaSuccess)
       return M5_ERR_CUDA;
-    attr_set = true;
+    once.done(bit);
   }
   const int m_tiles = (g.M + 2 * C2_BM - 1) / (2 * C2_BM);
   const int n_tiles = (g.N + C2_BN - 1) / C2_BN;

@@ -112,7 +112,8 @@ static int attn_block(m5_ctx* ctx, float* x, const SeqSet& seqs, int D, int H, i
   const bool split = mode != M5_NUM_FAST;
   // mixed: sequences long enough for the tcgen05 kernel keep Q (and P) single fp16 and carry K, V, O as pairs; shorter
   // ones (text encoder, tiny inputs) run the fully split mma.sync kernel
-  const bool tc5_split = mode == M5_NUM_MIXED && seqs.max_len >= 256;
+  // (below ~1k rows the probabilities' fp16 rounding is averaged over too few keys: uncond pass at S = 300 measured 7e-4)
+  const bool tc5_split = mode == M5_NUM_MIXED && seqs.max_len >= 1024;
   const bool q_pair = split && !tc5_split;   // does the attention kernel consume low halves of Q?
   const int qn = cross ? D : 3 * D;  // width of the projection of h16
   GemmCall gq = lin(s.h16, rows, D, split && !(cross && tc5_split), in_w, qn, in_b);

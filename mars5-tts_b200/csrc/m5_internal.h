@@ -4,9 +4,24 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/mars5_b200.h"
 
 namespace m5 {
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE attribute: a launcher keeps one bit per device (a second
+// context on another GPU of the same process must opt in again).  Setting the attribute twice from racing threads is harmless.
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool needed(unsigned long long& bit) const {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bit = 1ull << (dev & 63);
+    return (mask.load(std::memory_order_acquire) & bit) == 0;
+  }
+  void done(unsigned long long bit) { mask.fetch_or(bit, std::memory_order_release); }
+};
 
 // ---- tcgen05 GEMM (gemm_tc5.cu) ----------------------------------------------------------------
 enum { M5_OUT_F32 = 0, M5_OUT_F16 = 1, M5_OUT_SWIGLU_F16 = 2, M5_OUT_F16_SPLIT = 3, M5_OUT_SWIGLU_F16_SPLIT = 4 };

@@ -94,8 +94,14 @@ static int build_plan(m5_ctx* ctx, Arena& ar, NarPlan& p, int B, const int* c_te
   p.Nx.assign(x_len, x_len + B);
   p.S.resize(B); p.x_off.resize(B);
   p.Rx = 0; p.sum_Nx = 0;
+  const int max_pos = ctx->cfg.max_pos;
   for (int b = 0; b < B; ++b) {
     p.S[b] = (deep ? p.Pf[b] : 0) + p.Nx[b];
+    // the sinusoidal tables (tab.pe_nar) hold max_pos rows; the reference grows its table on demand
+    // (SinePositionalEmbedding.extend_pe, nn_future.py:51-76) -- here a longer sequence is an error, not a silent overrun
+    if (p.S[b] > max_pos || 1 + p.n_text[b] > max_pos || 1 + p.Pf[b] > max_pos || p.Nx[b] < 0 || p.Pf[b] < 0 || p.n_text[b] < 0)
+      return ctx->fail(M5_ERR_ARG, "utterance " + std::to_string(b) + ": sequence of " + std::to_string(std::max(p.S[b], std::max(1 + p.n_text[b], 1 + p.Pf[b]))) +
+                                       " positions exceeds m5_model_cfg.max_pos = " + std::to_string(max_pos) + " (rows of the positional tables)");
     p.x_off[b] = p.Rx;
     p.Rx += p.S[b];
     p.sum_Nx += p.Nx[b];

@@ -26,26 +26,41 @@ def _unflatten(blob, manifest):
     return out
 
 
+def _device(local):
+    """int / "cuda:N" -> that GPU (NCCL); "cpu" -> host tensors (gloo, the CPU test-suite)."""
+    return torch.device("cuda", local) if isinstance(local, int) else torch.device(local)
+
+
+def broadcast_packed(packed, rank, world, local):
+    """ONE broadcast of the repacked weight blob from rank 0 (plus a small object broadcast of its manifest).  `packed` is
+    the dict Engine takes ({"dims", "alphas", "tensors", "max_pos"}) on rank 0 and ignored elsewhere; every rank returns
+    that dict with tensors living on its own device (views into the received blob)."""
+    import torch.distributed as td
+    if world == 1:
+        return packed
+    dev = _device(local)
+    meta = [None]
+    if rank == 0:
+        blob, manifest = _flatten(packed["tensors"])
+        meta = [(packed["dims"], packed["alphas"], manifest, blob.numel(), packed["max_pos"])]
+    td.broadcast_object_list(meta, src=0)
+    dims, alphas, manifest, nbytes, max_pos = meta[0]
+    dblob = blob.to(dev) if rank == 0 else torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    td.broadcast(dblob, src=0)
+    return {"dims": dims, "alphas": alphas, "tensors": _unflatten(dblob, manifest), "max_pos": max_pos}
+
+
 def build_or_receive_weights(size, rank, world, local, max_pos=4096, seed=0):
     """Rank 0 builds the synthetic reference-format checkpoints and repacks them; every other rank receives the packed
-    blob with ONE ncclBroadcast (weights never touch the other ranks' host memory)."""
+    blob with ONE broadcast (weights never touch the other ranks' host memory)."""
     from . import synth, weights
-    dev = torch.device("cuda", local)
-    meta = [None]
+    packed = None
     if rank == 0:
         ar_sd, nar_sd, voc_sd = synth.make_ar_state(size, seed), synth.make_nar_state(size, seed + 1), synth.make_vocos_state(size, seed + 2)
         dims = weights.dims_from_state(ar_sd, nar_sd, voc_sd, size["n_text"])
         tensors, alphas = weights.repack(ar_sd, nar_sd, voc_sd, dims, max_pos=max_pos)
-        if world == 1:
-            return {"dims": dims, "alphas": alphas, "tensors": tensors, "max_pos": max_pos}
-        blob, manifest = _flatten(tensors)
-        meta = [(dims, alphas, manifest, blob.numel())]
-    import torch.distributed as td
-    td.broadcast_object_list(meta, src=0)
-    dims, alphas, manifest, nbytes = meta[0]
-    dblob = blob.to(dev) if rank == 0 else torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    td.broadcast(dblob, src=0)
-    return {"dims": dims, "alphas": alphas, "tensors": _unflatten(dblob, manifest), "max_pos": max_pos}
+        packed = {"dims": dims, "alphas": alphas, "tensors": tensors, "max_pos": max_pos}
+    return broadcast_packed(packed, rank, world, local)
 
 
 def shard_utterances(costs, world):
@@ -61,10 +76,11 @@ def shard_utterances(costs, world):
 
 
 def all_gather_waveforms(wavs, local):
-    """All-gather of variable-length waveforms: lengths first, then one padded (B, max_len) fp32 tensor per rank."""
+    """All-gather of variable-length waveforms: lengths first, then one padded (B, max_len) fp32 tensor per rank.
+    Returns (list over ranks of padded (B_r, max_len) tensors, list over ranks of length tensors)."""
     import torch.distributed as td
     world = td.get_world_size()
-    dev = torch.device("cuda", local)
+    dev = _device(local)
     lens = torch.tensor([len(w) for w in wavs], dtype=torch.int64, device=dev)
     all_lens = [torch.empty_like(lens) for _ in range(world)]
     td.all_gather(all_lens, lens)

@@ -33,34 +33,31 @@ def test_flatten_roundtrip():
 
 
 def _worker(rank, world, port, q):
+    """Drives the PRODUCT functions (dist.build_or_receive_weights / broadcast_packed / all_gather_waveforms /
+    shard_utterances) over gloo with CPU tensors -- the same code bench.py and the engine run over NCCL."""
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     td.init_process_group("gloo", rank=rank, world_size=world)
-    from mars5_tts_b200 import dist
-    # weight blob: rank 0 flattens, everybody receives the same bytes
-    meta = [None]
-    if rank == 0:
-        g = torch.Generator().manual_seed(0)
-        tensors = {"w": torch.randn(33, 17, generator=g).half(), "b": torch.randn(9, generator=g)}
-        blob, man = dist._flatten(tensors)
-        meta = [(man, blob.numel())]
-    td.broadcast_object_list(meta, src=0)
-    man, n = meta[0]
-    buf = blob if rank == 0 else torch.empty(n, dtype=torch.uint8)
-    td.broadcast(buf, src=0)
-    got = dist._unflatten(buf, man)
-    # waveform gather on CPU tensors (same code path as the NCCL one, device-agnostic parts)
-    wavs = [torch.full((100 + 10 * rank + i,), float(rank * 10 + i)) for i in range(2)]
-    lens = torch.tensor([len(w) for w in wavs])
-    all_lens = [torch.empty_like(lens) for _ in range(world)]
-    td.all_gather(all_lens, lens)
-    mx = int(max(int(l.max()) for l in all_lens))
-    pad = torch.zeros(2, mx)
-    for i, w in enumerate(wavs):
-        pad[i, :len(w)] = w
-    out = [torch.empty_like(pad) for _ in range(world)]
-    td.all_gather(out, pad)
-    q.put((rank, float(got["w"].float().sum()), [int(x) for l in all_lens for x in l], float(out[1 - rank][1, 0])))
+    from mars5_tts_b200 import dist, synth
+    packed = dist.build_or_receive_weights(synth.TINY, rank, world, "cpu", max_pos=64)
+    chk = float(sum(v.double().abs().sum() for v in packed["tensors"].values()))
+    n_t = len(packed["tensors"])
+    # sharding: every rank computes the same deterministic assignment, takes its own shard, "synthesises" waveforms whose
+    # content encodes the GLOBAL utterance id, and the all-gather must hand every rank every utterance exactly once
+    costs = [float((7 * i) % 13 + 1) for i in range(9)]
+    shards = dist.shard_utterances(costs, world)
+    mine = shards[rank]
+    wavs = [torch.full((50 + 3 * u,), float(u)) for u in mine]
+    out, all_lens = dist.all_gather_waveforms(wavs, "cpu")
+    seen = {}
+    for r in range(world):
+        for j, u in enumerate(shards[r]):
+            n = int(all_lens[r][j])
+            w = out[r][j, :n]
+            assert n == 50 + 3 * u and bool((w == float(u)).all()), (r, j, u)
+            assert bool((out[r][j, n:] == 0).all())
+            seen[u] = n
+    q.put((rank, chk, n_t, sorted(seen), packed["dims"]["ar_dim"], packed["max_pos"]))
     td.destroy_process_group()
 
 
@@ -71,10 +68,10 @@ def test_two_rank_gloo_broadcast_and_gather():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=120) for _ in range(2))
+    res = sorted(q.get(timeout=300) for _ in range(2))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert res[0][1] == res[1][1]                        # identical weights on both ranks
-    assert res[0][2] == res[1][2] == [100, 101, 110, 111]
-    assert res[0][3] == 11.0 and res[1][3] == 1.0         # each rank sees the other's second waveform
+    assert res[0][1] == res[1][1] and res[0][2] == res[1][2] > 50      # identical packed weights on both ranks
+    assert res[0][3] == res[1][3] == list(range(9))                     # every utterance reached every rank exactly once
+    assert res[0][4] == res[1][4] == 192 and res[0][5] == res[1][5] == 64

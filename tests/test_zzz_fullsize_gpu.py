@@ -159,7 +159,7 @@ def test_flash_attention_split_kv(m5lib, bare_ctx):
             e_split = max(e_split, ((O[q0:q0 + qn].float() + Ol[q0:q0 + qn].float()) - ref).abs().max().item())
             e_plain = max(e_plain, (Op[q0:q0 + qn].float() - ref).abs().max().item())
         print(f"split-KV attention: max-abs {e_split:.2e} (plain fp16 kernel {e_plain:.2e}), keys {k_lens}")
-        assert e_split < 6e-4 and e_split < 0.5 * e_plain, (k_lens, e_split, e_plain)
+        assert e_split < 1e-3 and e_split < 0.5 * e_plain, (k_lens, e_split, e_plain)
 
 
 # ------------------------------------------------------------------------------------------------ full-size pipelines
@@ -191,16 +191,18 @@ def test_nar_forward_full_dims_absolute_tolerance(full_engine):
     codes = torch.randint(0, 1024, (Pf, 8), generator=g)
     x = torch.randint(0, 1025, (S, 8), generator=g)
     torch.set_num_threads(min(32, torch.get_num_threads()))
-    ref = nar_oracle.nar_forward(nar_sd, cfg, text, codes, x, t).numpy()
-    scale = float(np.abs(ref).max())
-    errs = {}
-    for name, mode in (("fast", cp.NUM_FAST), ("mixed", cp.NUM_MIXED), ("precise", cp.NUM_PRECISE)):
-        got = eng.nar_forward([text.numpy()], [codes.numpy()], [x.numpy()], t, precise=mode)[0]
-        errs[name] = float(np.abs(got - ref).max())
-    print(f"NAR logits at full dims (S={S}): max|logit| {scale:.2f}; max-abs error " + ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
-    assert errs["mixed"] < 1e-3, errs
-    assert errs["precise"] < 1e-3, errs
-    assert errs["fast"] < 1e-3 * max(1.0, scale), errs
+    for drop in (False, True):   # conditional and unconditional pass of the classifier-free guidance pair
+        ref = nar_oracle.nar_forward(nar_sd, cfg, text, codes, x, t, drop_cond=drop).numpy()
+        scale = float(np.abs(ref).max())
+        errs = {}
+        for name, mode in (("fast", cp.NUM_FAST), ("mixed", cp.NUM_MIXED), ("precise", cp.NUM_PRECISE)):
+            got = eng.nar_forward([text.numpy()], [codes.numpy()], [x.numpy()], t, drop_cond=drop, precise=mode)[0]
+            errs[name] = float(np.abs(got - ref).max())
+        print(f"NAR logits at full dims (S={S}, drop_cond={drop}): max|logit| {scale:.2f}; max-abs error " +
+              ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
+        assert errs["mixed"] < 1e-3, errs
+        assert errs["precise"] < 1e-3, errs
+        assert errs["fast"] < 1e-3 * max(1.0, scale), errs
 
 
 def test_nar_forward_full_dims_uncond_and_batch(full_engine):
