@@ -44,9 +44,9 @@ M5_DEVINL uint4 ad_ldg_stream(const void* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
-M5_DEVINL unsigned ad_ld_acquire(const unsigned* p) {
+M5_DEVINL unsigned ad_ld_relaxed(const unsigned* p) {   // L2 poll without the L1 invalidation an acquire load implies
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -59,10 +59,10 @@ M5_DEVINL void grid_sync(unsigned* bar, unsigned& epoch, unsigned long long* pro
     epoch += gridDim.x;
     __threadfence();
     atomicAdd(bar, 1u);
-    if (ad_ld_acquire(bar) < epoch) {
+    if (ad_ld_relaxed(bar) < epoch) {
       const uint64_t t0 = global_timer_ns();
       uint32_t spins = 0;
-      while (ad_ld_acquire(bar) < epoch) {
+      while (ad_ld_relaxed(bar) < epoch) {
         if ((++spins & 0x3FF) == 0 && global_timer_ns() - t0 > 2000000000ull) {
           printf("m5: ar_decode grid barrier timed out (block %d, epoch %u)\n", blockIdx.x, epoch);
           __trap();
@@ -200,14 +200,19 @@ M5_DEVINL void gemm_phase(const ArDecodeParams& p, const ArGemm& g, const float*
     float acc[NT][4];
 #pragma unroll
     for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    // rolling prefetch: slot u always holds chunk c0 + u; as soon as its two MMAs per batch tile are issued the slot is
+    // refilled with chunk c0 + u + AD_UNROLL, so AD_UNROLL chunks (12 x 16 B per lane) stay in flight for the whole slice
     for (int c0 = 0; c0 < chunks; c0 += AD_UNROLL) {
-      if (c0 > 0) gemm_fetch(g, it, c0, pre);
 #pragma unroll
       for (int u = 0; u < AD_UNROLL; ++u) {
         const int c = c0 + u;
         if (c < chunks) {
           const uint32_t a1[4] = {pre.a[u].x, pre.b[u].x, pre.a[u].y, pre.b[u].y};
           const uint32_t a2[4] = {pre.a[u].z, pre.b[u].z, pre.a[u].w, pre.b[u].w};
+          if (c + AD_UNROLL < chunks) {
+            pre.a[u] = ad_ldg_stream(it.w0 + (c + AD_UNROLL) * 32);
+            pre.b[u] = ad_ldg_stream(it.w1 + (c + AD_UNROLL) * 32);
+          }
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
             const uint4 x = *reinterpret_cast<const uint4*>(xs + (size_t)(nt * 8 + gq) * xstride + (c * 32 + 8 * t) * 2);
@@ -385,28 +390,13 @@ M5_DEVINL void attn_phase(const ArDecodeParams& p, const ArLayerDev& lw, const C
     float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    auto fold = [&](const uint4& kv, const uint4& vv, bool ok) {
+    // partial dot product of this lane's 8 dims with one key row; the 8 lanes of a key group are summed by the caller
+    auto dot8 = [&](const uint4& kv) {
       const __half2* kh = reinterpret_cast<const __half2*>(&kv);
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(kh[i]); s += q[2 * i] * f.x + q[2 * i + 1] * f.y; }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      if (ok) {
-        s *= sl2;
-        const float mn = fmaxf(m, s);
-        const float c = exp2f(m - mn), pe = exp2f(s - mn);
-        l = l * c + pe;
-        const __half2* vh = reinterpret_cast<const __half2*>(&vv);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __half22float2(vh[i]);
-          acc[2 * i] = acc[2 * i] * c + pe * f.x;
-          acc[2 * i + 1] = acc[2 * i + 1] * c + pe * f.y;
-        }
-        m = mn;
-      }
+      return s;
     };
     const int n_tiles = (it.n_cache + AD_KT - 1) / AD_KT;
     for (int t = 0; t < n_tiles; ++t) {
@@ -415,12 +405,46 @@ M5_DEVINL void attn_phase(const ArDecodeParams& p, const ArLayerDev& lw, const C
       const uint8_t* sk = ring + sg * AD_STAGE_BYTES;
       const uint8_t* sv = sk + AD_KT * 128;
       const int kvalid = it.n_cache - t * AD_KT;   // keys of this tile that exist (>= 1)
+      // blocked online softmax over the tile: this lane's key group sees keys u * 4 + grp, u = 0 .. 7.  All 8 scores first
+      // (independent dot products and shuffles), ONE new running maximum, one rescale of (l, acc), then the 8 weighted
+      // value rows -- instead of 8 serially dependent (max, rescale, accumulate) updates
+      float sc[AD_KT / 4];
+#pragma unroll
+      for (int u = 0; u < AD_KT / 4; ++u) sc[u] = dot8(*reinterpret_cast<const uint4*>(sk + (u * 4 + grp) * 128 + sub * 16));
+#pragma unroll
+      for (int u = 0; u < AD_KT / 4; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], 1);
+#pragma unroll
+      for (int u = 0; u < AD_KT / 4; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], 2);
+      float mt = -INFINITY;
 #pragma unroll
       for (int u = 0; u < AD_KT / 4; ++u) {
-        const int kr = u * 4 + grp;
-        const uint4 kv = *reinterpret_cast<const uint4*>(sk + kr * 128 + sub * 16);
-        const uint4 vv = *reinterpret_cast<const uint4*>(sv + kr * 128 + sub * 16);
-        fold(kv, vv, kr < kvalid);
+        sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], 4);
+        sc[u] = (u * 4 + grp < kvalid) ? sc[u] * sl2 : -INFINITY;
+        mt = fmaxf(mt, sc[u]);
+      }
+      const float mn = fmaxf(m, mt);
+      if (mn > -INFINITY) {   // (a group may own no valid key of a short tile while it is still empty)
+        const float c = exp2f(m - mn);
+        float ps = 0.f, pa[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pa[i] = 0.f;
+#pragma unroll
+        for (int u = 0; u < AD_KT / 4; ++u) {
+          const float pe = exp2f(sc[u] - mn);
+          ps += pe;
+          const uint4 vv = *reinterpret_cast<const uint4*>(sv + (u * 4 + grp) * 128 + sub * 16);
+          const __half2* vh = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(vh[i]);
+            pa[2 * i] += pe * f.x;
+            pa[2 * i + 1] += pe * f.y;
+          }
+        }
+        l = l * c + ps;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = acc[i] * c + pa[i];
+        m = mn;
       }
       __syncwarp();            // every lane has read the stage: it may be refilled
       ++st.consumed;
@@ -449,7 +473,24 @@ M5_DEVINL void attn_phase(const ArDecodeParams& p, const ArLayerDev& lw, const C
         *reinterpret_cast<uint4*>(p.kc + coff) = kn;
         *reinterpret_cast<uint4*>(p.vc + coff) = vn;
       }
-      fold(kn, vn, grp == 0);
+      float s = dot8(kn);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (grp == 0) {
+        s *= sl2;
+        const float mn = fmaxf(m, s);
+        const float c = exp2f(m - mn), pe = exp2f(s - mn);
+        l = l * c + pe;
+        const __half2* vh = reinterpret_cast<const __half2*>(&vn);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(vh[i]);
+          acc[2 * i] = acc[2 * i] * c + pe * f.x;
+          acc[2 * i + 1] = acc[2 * i + 1] * c + pe * f.y;
+        }
+        m = mn;
+      }
     }
     // merge the 4 key groups of the warp (fixed order), write the split partial (m, l, acc[64])
     float M = fmaxf(fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8)), fmaxf(__shfl_xor_sync(0xffffffffu, m, 16), __shfl_xor_sync(0xffffffffu, m, 24)));

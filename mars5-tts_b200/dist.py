@@ -76,18 +76,27 @@ def shard_utterances(costs, world):
 
 
 def all_gather_waveforms(wavs, local):
-    """All-gather of variable-length waveforms: lengths first, then one padded (B, max_len) fp32 tensor per rank.
-    Returns (list over ranks of padded (B_r, max_len) tensors, list over ranks of length tensors)."""
+    """All-gather of variable-length waveforms from shards of possibly DIFFERENT sizes (mixed-length batches, LPT sharding):
+    the per-rank utterance counts first, then the lengths (padded to the largest count), then one padded
+    (max_count, max_len) fp32 tensor per rank.
+    Returns (list over ranks of (B_r, max_len) tensors, list over ranks of (B_r,) length tensors)."""
     import torch.distributed as td
     world = td.get_world_size()
     dev = _device(local)
-    lens = torch.tensor([len(w) for w in wavs], dtype=torch.int64, device=dev)
+    cnt = torch.tensor([len(wavs)], dtype=torch.int64, device=dev)
+    cnts = [torch.empty_like(cnt) for _ in range(world)]
+    td.all_gather(cnts, cnt)
+    counts = [int(c.item()) for c in cnts]
+    mc = max(counts)
+    lens = torch.zeros(mc, dtype=torch.int64, device=dev)
+    if len(wavs):
+        lens[:len(wavs)] = torch.tensor([len(w) for w in wavs], dtype=torch.int64, device=dev)
     all_lens = [torch.empty_like(lens) for _ in range(world)]
     td.all_gather(all_lens, lens)
-    mx = int(max(int(l.max()) for l in all_lens)) if len(wavs) else 0
-    pad = torch.zeros(len(wavs), mx, dtype=torch.float32, device=dev)
+    mx = int(max(int(l.max()) for l in all_lens)) if mc else 0
+    pad = torch.zeros(mc, mx, dtype=torch.float32, device=dev)
     for i, w in enumerate(wavs):
         pad[i, :len(w)] = torch.as_tensor(w, device=dev) if not torch.is_tensor(w) else w.to(dev)
     out = [torch.empty_like(pad) for _ in range(world)]
     td.all_gather(out, pad)
-    return out, all_lens
+    return [o[:c] for o, c in zip(out, counts)], [l[:c] for l, c in zip(all_lens, counts)]

@@ -27,7 +27,7 @@ n_text = size["n_text"]
 prompts = [torch.randint(n_text, n_text + 1024, (args.P,), generator=g).numpy().astype(np.int32) for _ in range(args.B)]
 spk = [torch.randint(0, 1024, (450, 8), generator=g).numpy().astype(np.int32) for _ in range(args.B)]
 eos = eng.dims["ar_vocab"] - 1
-acfg = eng.make_ar_cfg(InferenceConfig(), args.P + args.N + 2, eos, force_len=args.N, sync_every=64)
+acfg = eng.make_ar_cfg(InferenceConfig(), args.P + args.N + 2, eos, force_len=args.N + 8, sync_every=64)  # rows still running at the last step: its profile is a normal step
 peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
     os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6569.6
 for rep in range(3):
