@@ -272,6 +272,55 @@ def cpu_port_sample(size, wl, T, budget_s=25.0):
     return audio / total, detail, sample
 
 
+def gpu_eager_sample(size, wl, T, device):
+    """Same-box GPU baseline (last bullet): the reference's arithmetic as plain PyTorch eager on
+    THIS GPU -- the oracle port moved to the device (cuBLAS / torch kernels, none of this repo's), batch 1 like the
+    reference: KV-cached AR steps at the mean context under fp16 autocast (inference.py:263), fp32 NAR evaluations
+    (diffuser.py:358) and the posterior; 32 utterances = 32 sequential calls.  Bounded sample, extrapolated like
+    cpu_port_sample.  A stated baseline beside the headline, not part of the product path."""
+    from mars5_tts_b200 import synth, weights
+    from oracle import ar_oracle, nar_oracle
+    dev = torch.device("cuda", device)
+    ar_sd = {k: v.to(dev) for k, v in synth.make_ar_state(size).items()}
+    nar_sd = {k: v.to(dev) for k, v in synth.make_nar_state(size).items()}
+    cfg = weights.dims_from_state(ar_sd, nar_sd, None, size["n_text"])
+    prompt, spk, text = (torch.from_numpy(wl[k][0]).long().to(dev) for k in ("prompts", "spk", "text"))
+    N, Pf = wl["N_b"][0], wl["Pf"]
+    sync = torch.cuda.synchronize
+    with torch.inference_mode(), torch.device(dev):
+        L_mean, H = len(prompt) + 1 + N // 2, cfg["ar_heads"]
+        cache = ar_oracle.KVCache()
+        for l in range(cfg["ar_layers"]):
+            cache.k[l] = torch.randn(L_mean, H, 64, device=dev)
+            cache.v[l] = torch.randn(L_mean, H, 64, device=dev)
+        cache.n = L_mean
+        tok = torch.randint(size["n_text"], cfg["ar_vocab"], (1,), device=dev)
+        with torch.autocast("cuda", dtype=torch.float16):
+            for _ in range(2):
+                ar_oracle.codeclm_step(ar_sd, cfg, tok, spk, cache)
+            sync(); t0 = time.perf_counter()
+            for _ in range(5):
+                ar_oracle.codeclm_step(ar_sd, cfg, tok, spk, cache)
+            sync(); t_ar = (time.perf_counter() - t0) / 5
+        del cache
+        S = Pf + (Pf - 1 + N)
+        x = torch.randint(0, 1025, (S, 8), device=dev)
+        nar_oracle.nar_forward(nar_sd, cfg, text, spk, x, T // 2)
+        sync(); t0 = time.perf_counter()
+        logits = nar_oracle.nar_forward(nar_sd, cfg, text, spk, x, T // 2)
+        sync(); t_fwd = time.perf_counter() - t0
+        tabs = tuple(t_.to(dev) for t_ in nar_oracle.diffusion_tables(T))
+        K = cfg["n_classes"]
+        u = torch.rand(2, S, 8, K, device=dev)
+        xk, m = torch.zeros_like(x), torch.zeros_like(x).bool()
+        sync(); t0 = time.perf_counter()
+        nar_oracle.reverse_step(tabs, logits, logits, x, xk, m, T // 2, 3.0, 0.7, u[0], u[1], K)
+        sync(); t_post = time.perf_counter() - t0
+    total = N * t_ar + T * (2 * t_fwd + t_post)
+    return ((N - 1) / 75.0) / total, {"t_ar_step_s": round(t_ar, 5), "t_nar_forward_s": round(t_fwd, 4), "t_posterior_s": round(t_post, 4),
+                                     "extrapolated_s_per_utterance": round(total, 2)}
+
+
 def reference_c1_sample(T_sample=2, budget_s=120.0):
     """The UNMODIFIED reference (/root/reference/mars5: ar_generate + perform_simple_inference) on BASELINE configs[0]
     (shallow clone, 6 s reference, 10-word prompt, batch 1, CPU fp32), full-size random weights; AR for a bounded number
@@ -537,8 +586,19 @@ def main():
         out["fast_mode"] = {"value": wl["audio_s"] * world / (fast_ms / 1e3), "unit": UNIT, "steps": 1,
                             "note": "nar_numerics=fast (fp16 operands everywhere): does NOT meet the 1e-3 max-abs logit bound"}
     if world == 1 and not args.no_cpu_baseline:
-        v, detail, samp = cpu_port_sample(size, make_workload(size, 1, 1234, **wl_kw), T, budget_s=25.0)
+        wl1 = make_workload(size, 1, 1234, **wl_kw)
+        v, detail, samp = cpu_port_sample(size, wl1, T, budget_s=25.0)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "kind": "port", "sample": samp, **detail}
+        if BUDGET_S - elapsed() > 60:
+            try:   # never a reason to lose the line
+                eng.close()
+                del eng
+                torch.cuda.empty_cache()
+                gv, gd = gpu_eager_sample(size, wl1, T, local)
+                out["gpu_eager_baseline"] = {"value": gv, "unit": UNIT, "kind": "oracle port in PyTorch eager on this GPU, batch 1 (fp16-autocast AR, "
+                                             "fp32 NAR): the reference's own execution model, 32 utterances = 32 sequential calls", **gd}
+            except Exception as e:
+                out["gpu_eager_baseline"] = {"unavailable": repr(e)[:300]}
     out["wall_s"] = round(elapsed(), 1)
     print(json.dumps(out))
 

@@ -162,6 +162,14 @@ int m5_ar_forward(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int32
 int m5_vocode(m5_ctx* ctx, int32_t B, const int32_t* codes, const int32_t* n_frames, int32_t bandwidth_id,
               int32_t mem, float* wav_out);
 
+/* Vocoder + silence trim without leaving the device (inference.py:304-305: trim(vocode(tokens), top_db=cfg.trim_db),
+ * mars5/trim.py:110-177).  wav_out receives the UNTRIMMED waveforms exactly like m5_vocode; start / end [B] (HOST) receive
+ * the sample range of utterance b inside its own waveform -- the same numbers m5_trim_bounds returns for it (frame powers
+ * over frame_length-sample frames every hop_length samples of the reflect-padded signal, top_db below the loudest frame). */
+int m5_vocode_trim(m5_ctx* ctx, int32_t B, const int32_t* codes, const int32_t* n_frames, int32_t bandwidth_id,
+                   int32_t mem, float top_db, int32_t frame_length, int32_t hop_length, float* wav_out, int64_t* start,
+                   int64_t* end);
+
 /* ---- Tokenisers either side of the path (host code, no GPU work) ----------------------------
  * Merge engine for the two "minbpe v1" tokenisers: text (base = 256 bytes, mars5/minbpe/regex.py) and speech
  * (base = 1024 Encodec L0 codes, mars5/minbpe/codebook.py).  The regex split of text into chunks and the special-token

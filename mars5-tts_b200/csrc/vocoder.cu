@@ -76,8 +76,67 @@ using namespace m5;
 
 extern "C" {
 
-int m5_vocode(m5_ctx* ctx, int32_t B, const int32_t* codes, const int32_t* n_frames, int32_t bandwidth_id, int32_t mem,
-              float* wav_out) {
+// Silence trim on the device, right behind the overlap-add (inference.py:304-305 -> mars5/trim.py:110-177): the waveform is
+// still in HBM, so the frame powers are one more pass over it instead of a host loop over a copied buffer.
+//   trim_power_kernel : one warp per 2048-sample frame (hop 512) of the reflect-padded waveform, mean square in double
+//   trim_bounds_kernel: one CTA per utterance: loudest frame, then the first / last frame within top_db of it --
+//                       10 log10(max(1e-10, p_f)) - 10 log10(max(1e-10, max_f p_f)) > -top_db, evaluated in double exactly
+//                       like the host entry point m5_trim_bounds (trim.cu)
+__global__ void trim_power_kernel(const float* wav, const long long* off, const int* frame0, int B, int frame_length, int hop,
+                                  double* power) {
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int total = frame0[B];
+  if (gw >= total) return;
+  int b = 0;
+  while (b + 1 < B && frame0[b + 1] <= gw) ++b;
+  const int f = gw - frame0[b];
+  const float* y = wav + off[b];
+  const long long n = off[b + 1] - off[b], pad = frame_length / 2;
+  double s = 0.0;
+  for (int i = lane; i < frame_length; i += 32) {
+    long long j = (long long)f * hop + i - pad;   // index into the unpadded signal; reflect without repeating the edge
+    if (j < 0) j = -j;
+    else if (j >= n) j = 2 * (n - 1) - j;
+    const double v = (double)y[j];
+    s += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) power[gw] = s / (double)frame_length;
+}
+__global__ void trim_bounds_kernel(const double* power, const long long* off, const int* frame0, int hop, double top_db,
+                                   long long* start, long long* end) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const double* p = power + frame0[b];
+  const int nfr = frame0[b + 1] - frame0[b];
+  __shared__ double s_max[256];
+  __shared__ int s_first[256], s_last[256];
+  double mx = 0.0;
+  for (int f = tid; f < nfr; f += blockDim.x) mx = fmax(mx, p[f]);
+  s_max[tid] = mx;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) { if (tid < o) s_max[tid] = fmax(s_max[tid], s_max[tid + o]); __syncthreads(); }
+  const double ref_db = 10.0 * log10(fmax(1e-10, s_max[0]));
+  int first = 0x7FFFFFFF, last = -1;
+  for (int f = tid; f < nfr; f += blockDim.x) {
+    const double db = 10.0 * log10(fmax(1e-10, p[f])) - ref_db;
+    if (db > -top_db) { first = min(first, f); last = max(last, f); }
+  }
+  s_first[tid] = first; s_last[tid] = last;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if (tid < o) { s_first[tid] = min(s_first[tid], s_first[tid + o]); s_last[tid] = max(s_last[tid], s_last[tid + o]); }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const long long n = off[b + 1] - off[b];
+    if (s_last[0] < 0) { start[b] = 0; end[b] = 0; }   // "the signal only contains zeros"
+    else { start[b] = (long long)s_first[0] * hop; end[b] = min(n, (long long)(s_last[0] + 1) * hop); }
+  }
+}
+
+static int vocode_impl(m5_ctx* ctx, int32_t B, const int32_t* codes, const int32_t* n_frames, int32_t bandwidth_id, int32_t mem,
+                       float* wav_out, bool do_trim, float top_db, int frame_length, int hop_length, int64_t* t_start, int64_t* t_end) {
   if (!ctx || B <= 0) return M5_ERR_ARG;
   ctx->last_error.clear();
   cudaSetDevice(ctx->device);
@@ -152,9 +211,46 @@ int m5_vocode(m5_ctx* ctx, int32_t B, const int32_t* codes, const int32_t* n_fra
   gh.out = spec; gh.ldc = ldspec; gh.mode = M5_OUT_F32;
   M5_TRY(run_gemm(ctx, gh));
   M5_TRY(istft_run(ctx, w, spec, ldspec, B, nf, frames, d_f0, d_nf, d_wav));
+  std::vector<long long> h_bounds;
+  long long* d_bounds = nullptr;
+  if (do_trim) {
+    // frames of every utterance: 1 + (n + 2 * (frame_length / 2) - frame_length) / hop   (centered, reflect padded)
+    std::vector<long long> off(B + 1, 0);
+    std::vector<int> fr0(B + 1, 0);
+    for (int b = 0; b < B; ++b) {
+      const long long n = (long long)nf[b] * 320;
+      if (n <= frame_length / 2) return ctx->fail(M5_ERR_ARG, "silence trim: a waveform must be longer than frame_length / 2 samples");
+      off[b + 1] = off[b] + n;
+      fr0[b + 1] = fr0[b] + (int)(1 + (n + 2 * (frame_length / 2) - frame_length) / hop_length);
+    }
+    long long* d_off = ar.get<long long>(B + 1); int* d_fr0 = ar.get<int>(B + 1);
+    double* d_pow = ar.get<double>(fr0[B]);
+    d_bounds = ar.get<long long>((size_t)2 * B);
+    if (!d_off || !d_fr0 || !d_pow || !d_bounds) return ctx->fail(M5_ERR_NOMEM, "arena too small (trim)");
+    cudaMemcpyAsync(d_off, off.data(), (B + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_fr0, fr0.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    trim_power_kernel<<<(fr0[B] + 7) / 8, 256, 0, ctx->stream>>>(d_wav, d_off, d_fr0, B, frame_length, hop_length, d_pow);
+    trim_bounds_kernel<<<B, 256, 0, ctx->stream>>>(d_pow, d_off, d_fr0, hop_length, (double)top_db, d_bounds, d_bounds + B);
+    ctx->launches += 2;
+    h_bounds.resize((size_t)2 * B);
+    M5_CUDA(cudaMemcpyAsync(h_bounds.data(), d_bounds, (size_t)2 * B * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  }
   if (mem == M5_MEM_HOST) M5_CUDA(cudaMemcpyAsync(wav_out, d_wav, (size_t)N * 320 * 4, cudaMemcpyDeviceToHost, ctx->stream));
   M5_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (do_trim)
+    for (int b = 0; b < B; ++b) { t_start[b] = h_bounds[b]; t_end[b] = h_bounds[B + b]; }
   return M5_OK;
+}
+
+int m5_vocode(m5_ctx* ctx, int32_t B, const int32_t* codes, const int32_t* n_frames, int32_t bandwidth_id, int32_t mem,
+              float* wav_out) {
+  return vocode_impl(ctx, B, codes, n_frames, bandwidth_id, mem, wav_out, false, 0.f, 0, 0, nullptr, nullptr);
+}
+
+int m5_vocode_trim(m5_ctx* ctx, int32_t B, const int32_t* codes, const int32_t* n_frames, int32_t bandwidth_id, int32_t mem,
+                   float top_db, int32_t frame_length, int32_t hop_length, float* wav_out, int64_t* start, int64_t* end) {
+  if (!start || !end || frame_length < 2 || hop_length < 1 || top_db < 0.f) return M5_ERR_ARG;
+  return vocode_impl(ctx, B, codes, n_frames, bandwidth_id, mem, wav_out, true, top_db, frame_length, hop_length, start, end);
 }
 
 // ------------------------------------------------------------------------------------------------ debug entry points

@@ -225,6 +225,19 @@ class Engine:
         capi.check(self.ctx, rc, "m5_vocode")
         return out
 
+    def vocode_trim(self, codes, top_db, bandwidth_id=1, frame_length=2048, hop_length=512):
+        """Vocoder + the reference's silence trim (inference.py:304-305) in one call; the frame powers are computed on the
+        device behind the overlap-add.  Returns (list of untrimmed waveforms, list of (start, end) sample ranges)."""
+        nf = [len(c) for c in codes]
+        cat, nf_a = _cat_i32(codes, 8), _i32(nf)
+        out = np.zeros((int(np.sum(nf)) * self.dims["voc_hop"],), dtype=np.float32)
+        st, en = np.zeros(len(nf), dtype=np.int64), np.zeros(len(nf), dtype=np.int64)
+        rc = self.lib.m5_vocode_trim(self.ctx, len(nf), capi.ptr(cat), capi.ptr(nf_a), int(bandwidth_id), capi.MEM_HOST, float(top_db),
+                                     int(frame_length), int(hop_length), capi.ptr(out), capi.ptr(st), capi.ptr(en))
+        capi.check(self.ctx, rc, "m5_vocode_trim")
+        offs = np.concatenate([[0], np.cumsum(nf)]) * self.dims["voc_hop"]
+        return [out[offs[b]:offs[b + 1]] for b in range(len(codes))], [(int(a), int(b)) for a, b in zip(st, en)]
+
     def vocode(self, codes, bandwidth_id=1):
         nf = [len(c) for c in codes]
         out = self.vocode_packed(_cat_i32(codes, 8), nf, bandwidth_id)
@@ -250,15 +263,35 @@ class Mars5TTS:
             texttok.load(ar_ckpt["vocab"]["texttok.model"])
             speechtok = bpe.CodebookTokenizer(bpe.GPT4_SPLIT_PATTERN)
             speechtok.load(ar_ckpt["vocab"]["speechtok.model"])
-        self.texttok, self.speechtok, self.codec = texttok, speechtok, codec
         dev_index = torch.device(device).index if device not in (None, "cuda") else None
         self.device = torch.device("cuda", dev_index or 0)
+        if codec is None:
+            # like the reference (inference.py:87-88): EncodecModel.encodec_model_24khz() at 6 kbps on the device.  The Encodec
+            # ENCODER is outside the hot path (third-party package); it is only needed by tts().
+            try:
+                from encodec import EncodecModel
+                codec = EncodecModel.encodec_model_24khz().to(self.device).eval()
+                codec.set_target_bandwidth(6.0)
+            except ImportError:
+                codec = None   # tts() raises with instructions; vocode() / the Engine keep working
+        if vocos_state is None:
+            # like the reference (inference.py:119-121): Vocos.from_pretrained("charactr/vocos-encodec-24khz"), weight norm
+            # folded; only its state dict is used -- the network itself runs in libmars5_b200.so
+            try:
+                from vocos import Vocos
+                vocos_state = Vocos.from_pretrained("charactr/vocos-encodec-24khz").state_dict()
+            except ImportError:
+                raise RuntimeError("the `vocos` package is not importable: pass vocos_state=<state dict of "
+                                   "Vocos.from_pretrained('charactr/vocos-encodec-24khz')> to Mars5TTS (the vocoder network runs "
+                                   "inside libmars5_b200.so, only its weights are needed)") from None
+        self.texttok, self.speechtok, self.codec = texttok, speechtok, codec
         self.engine = Engine(ar_ckpt["model"], nar_ckpt["model"], vocos_state, len(texttok.vocab), device=self.device.index)
         self.n_vocab = len(texttok.vocab) + len(speechtok.vocab)
         self.n_text_vocab = len(texttok.vocab) + 1
         self.diffusion_n_classes = 1025
         self.default_T = 200
         self.sr, self.latent_sr = 24000, 75
+        self._calls = 0   # tts() draws fresh randomness on every call, like the reference's unseeded torch generator
 
     @torch.inference_mode()
     def vocode(self, tokens: torch.Tensor) -> torch.Tensor:
@@ -280,7 +313,15 @@ class Mars5TTS:
         if ref_audio.shape[0] != 1:
             ref_audio = ref_audio.mean(dim=0, keepdim=True)
         ref_audio = torch.nn.functional.pad(ref_audio, (int(self.sr * cfg.ref_audio_pad), 0))
-        prompt_codec = self.codec.encode(ref_audio[None])[0][0]  # (1, n_q, T)
+        if self.codec is None:
+            raise RuntimeError("no Encodec codec: `encodec` is not importable and no codec= was passed to Mars5TTS "
+                               "(anything with encode(wav[None]) -> [(codes (1, 8, T), scale)] works)")
+        wav_in = ref_audio[None]
+        if hasattr(self.codec, "parameters"):   # an nn.Module codec lives on its own device (the reference moves the clip there)
+            p0 = next(iter(self.codec.parameters()), None)
+            if p0 is not None:
+                wav_in = wav_in.to(p0.device)
+        prompt_codec = self.codec.encode(wav_in)[0][0]  # (1, n_q, T)
         l0 = prompt_codec[0, 0].tolist()
         speech_tokens = self.speechtok.encode(" ".join(str(t) for t in l0).strip())
         spk_ref = prompt_codec[0].T.cpu().numpy().astype(np.int32)  # (T, n_q)
@@ -299,8 +340,11 @@ class Mars5TTS:
 
     @torch.inference_mode()
     def tts_batch(self, texts: List[str], ref_audios, ref_transcripts, cfg: InferenceConfig = InferenceConfig(),
-                  seed: int = 0):
-        """Batched tts(): every row equals a single reference call.  Returns a list of (L0 codes, waveform)."""
+                  seed: int = 0, utt_base: int = 0):
+        """Batched tts(): every row equals a single reference call.  Returns a list of (L0 codes, waveform).
+        Randomness: Philox streams keyed by (seed, utt_base + row) -- the same (seed, utterance id) reproduces the same audio
+        whatever the batch composition or the number of GPUs.  `cfg.use_kv_cache` is accepted for API parity; the engine
+        always uses its KV cache (the reference's two paths agree to 1e-6 on the logits)."""
         assert cfg.beam_width == 1, "Only beam size of 1 is currently supported."
         preps = [self._prepare(t, a, r, cfg) for t, a, r in zip(texts, ref_audios, ref_transcripts)]
         eng, tt = self.engine, self.texttok
@@ -312,7 +356,7 @@ class Mars5TTS:
             acfg = eng.make_ar_cfg(cfg, max_len, eos)
             ids, hit, _ = eng.ar_generate([p["prompt"] for p in chunk], [p["spk_ref"] for p in chunk],
                                           [p["n_phones"] for p in chunk], acfg, seed=seed,
-                                          utt_ids=list(range(s, s + len(chunk))))
+                                          utt_ids=list(range(utt_base + s, utt_base + s + len(chunk))))
             toks = []
             for p, seq, h in zip(chunk, ids, hit):
                 if h:
@@ -324,22 +368,32 @@ class Mars5TTS:
             l0s = [np.asarray([c for c in d if type(c) == int], dtype=np.int32) for d in dec]
             ncfg = eng.make_nar_cfg(cfg, T=self.default_T)
             codes = eng.nar_infer([p["text_tokens"] for p in chunk], [p["spk_ref"] for p in chunk], l0s, ncfg, seed=seed,
-                                  utt_ids=list(range(s, s + len(chunk))))
+                                  utt_ids=list(range(utt_base + s, utt_base + s + len(chunk))))
             outs = []
             for p, c in zip(chunk, codes):
                 skip = len(p["spk_ref"]) if cfg.deep_clone else 0  # second crop of inference.py:300-301
                 outs.append(c[skip:])
-            wavs = eng.vocode(outs, bandwidth_id=1)
-            # vocode final output and trim silences (inference.py:304-305), the whole chunk at once
-            bounds = trim_bounds_batch(wavs, top_db=cfg.trim_db)
+            # vocode final output and trim silences (inference.py:304-305): one call, the frame powers of the trim are
+            # computed on the device behind the overlap-add (utterances too short for a 2048-sample frame go to the host path,
+            # which raises like the reference does)
+            if all(len(o) * eng.dims["voc_hop"] > 1024 for o in outs):
+                wavs, bounds = eng.vocode_trim(outs, cfg.trim_db, bandwidth_id=1)
+            else:
+                wavs = eng.vocode(outs, bandwidth_id=1)
+                bounds = trim_bounds_batch(wavs, top_db=cfg.trim_db)
             for i, (l0, w, (a, b)) in enumerate(zip(l0s, wavs, bounds)):
                 results[s + i] = (torch.from_numpy(l0.astype(np.int64)).to(self.device), torch.from_numpy(w[a:b].copy()))
         return results
 
     @torch.inference_mode()
     def tts(self, text: str, ref_audio: torch.Tensor, ref_transcript: Optional[str] = None,
-            cfg: Optional[InferenceConfig] = InferenceConfig()):
+            cfg: Optional[InferenceConfig] = InferenceConfig(), seed: Optional[int] = None):
         """Same contract as the reference's tts() (inference.py:201-307): (AR L0 codes on the device, trimmed 24 kHz
-        waveform on the CPU)."""
-        codes, wav = self.tts_batch([text], [ref_audio], [ref_transcript], cfg)[0]
+        waveform on the CPU).  Like the reference (which never seeds torch), consecutive calls draw different randomness:
+        the Philox seed defaults to torch.initial_seed() and the utterance id to a per-object call counter, so
+        torch.manual_seed(s) before the first call makes a run reproducible; pass seed= for an explicit stream."""
+        if seed is None:
+            seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+        codes, wav = self.tts_batch([text], [ref_audio], [ref_transcript], cfg, seed=seed, utt_base=self._calls)[0]
+        self._calls += 1
         return codes, wav

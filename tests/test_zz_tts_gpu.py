@@ -45,8 +45,12 @@ def test_tts_batch_rows_equal_single_calls_and_hand_chained_stages(tts):
         assert codes.dtype == torch.long and codes.is_cuda and codes.dim() == 1 and codes.numel() > 0
         assert wav.dtype == torch.float32 and not wav.is_cuda and wav.dim() == 1 and torch.isfinite(wav).all()
     # single call == row 0 of the batch (results are keyed by utterance id, not by batch position or size)
-    c0, w0 = tts.tts(texts[0], refs[0], trs[0], cfg)
+    tts._calls = 0
+    c0, w0 = tts.tts(texts[0], refs[0], trs[0], cfg, seed=0)
     assert torch.equal(c0, out[0][0]) and torch.equal(w0, out[0][1])
+    # like the reference (unseeded torch generator) the next call draws fresh randomness: call counter -> utterance id
+    c1, w1 = tts.tts(texts[0], refs[0], trs[0], cfg, seed=0)
+    assert tts._calls == 2 and not (c1.numel() == c0.numel() and torch.equal(c1, c0) and torch.equal(w1, w0))
     # the same stages chained by hand through Engine
     eng = tts.engine
     preps = [tts._prepare(t, a, r, cfg) for t, a, r in zip(texts, refs, trs)]
@@ -64,3 +68,21 @@ def test_tts_batch_rows_equal_single_calls_and_hand_chained_stages(tts):
         assert got_codes.cpu().tolist() == l0.tolist()
         a, b = trim_oracle.trim_bounds(torch.from_numpy(w), cfg.trim_db)
         assert got_wav.numel() == b - a and torch.equal(got_wav, torch.from_numpy(w)[a:b])
+
+
+def test_device_trim_equals_host_trim_and_oracle(tts):
+    """m5_vocode_trim (frame powers on the device, behind the overlap-add) returns the very bounds of the host entry point
+    m5_trim_bounds and of the float32 oracle (pinned to the reference's own trim() by tests/golden/trim_golden.json) on
+    vocoder output of different lengths, including a near-silent one and an all-pad (constant) utterance."""
+    from mars5_tts_b200.trim import trim_bounds_batch
+    eng = tts.engine
+    g = torch.Generator().manual_seed(3)
+    codes = [torch.randint(0, 1024, (n, 8), generator=g).numpy().astype(np.int32) for n in (4, 9, 40, 150)]
+    codes.append(np.zeros((30, 8), dtype=np.int32))
+    for db in (27.0, 5.0, 60.0):
+        wavs, bounds = eng.vocode_trim(codes, db)
+        ref_wavs = eng.vocode(codes)
+        host = trim_bounds_batch(ref_wavs, top_db=db)
+        for w, rw, b, h in zip(wavs, ref_wavs, bounds, host):
+            assert np.array_equal(w, rw)
+            assert b == h == trim_oracle.trim_bounds(torch.from_numpy(rw), db), (db, b, h)
