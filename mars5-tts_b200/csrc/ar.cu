@@ -416,7 +416,7 @@ int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int3
   dp.B = B; dp.n_layers = L; dp.D = D; dp.F = F; dp.H = c.ar_heads; dp.V = V; dp.Wc = Wc; dp.eps = c.ar_norm_eps;
   dp.final_norm = w.norm; dp.embed = w.embed; dp.inv_freq = w.inv_freq;
   dp.ids = st.ids; dp.ids_stride = max_len; dp.tok_len = st.tok_len; dp.kv_len = st.kv_len; dp.done = st.done;
-  dp.x = st.x; dp.qkv = st.qkv32; dp.g16 = st.g16; dp.logits = st.logits; dp.kc = kc; dp.vc = vc;
+  dp.x = st.x; dp.qkv = st.qkv32; dp.g16 = st.g16; dp.att16 = st.att16; dp.logits = st.logits; dp.kc = kc; dp.vc = vc;
   M5_TRY(ar_decode_plan(dp, ctx->num_sms));
   dp.g_out.W = w.output;
   dp.n_split = ar_decode_splits_for(Wc);
@@ -428,8 +428,10 @@ int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int3
     dp.attn_part = ar.get<float>(ar_decode_attn_floats(B, c.ar_heads, dp.n_split));
     dp.scratch = ar.get<float>(ar_decode_scratch_floats(dp));
     dp.counters = ar.get<int>(ar_decode_max_tiles(dp) + 1);
+    dp.attn_tickets = ar.get<int>((size_t)B * c.ar_heads);
+    if (dp.attn_tickets) cudaMemsetAsync(dp.attn_tickets, 0, (size_t)B * c.ar_heads * sizeof(int), ctx->stream);
     dp.gbar = reinterpret_cast<unsigned*>(ar.get<int>(4));
-    if (!dp.layers || !dp.ssq || !dp.attn_part || !dp.scratch || !dp.counters || !dp.gbar)
+    if (!dp.layers || !dp.ssq || !dp.attn_part || !dp.scratch || !dp.counters || !dp.gbar || !dp.attn_tickets)
       return ctx->fail(M5_ERR_NOMEM, "arena too small (fused decode buffers)");
     cudaMemsetAsync(dp.counters, 0, (ar_decode_max_tiles(dp) + 1) * sizeof(int), ctx->stream);
     if (getenv("M5_AR_PROFILE")) {   // per-phase timeline of CTA 0 of the LAST decode step, printed to stderr after the loop

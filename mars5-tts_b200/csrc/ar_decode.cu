@@ -136,41 +136,13 @@ M5_DEVINL void stage_x(const ArDecodeParams& p, const ArGemm& g, int kbase, cons
       }
       *reinterpret_cast<uint2*>(xs + (size_t)row * xstride + c * 2) = o;
     }
-  } else if constexpr (XSRC == X_ATTN) {
-    // merge of the split-KV partials (m, l, acc[64]) in split order: one (row, head) per 32 lanes, 2 columns per lane
-    const int warp = tid >> 5, lane = tid & 31;
-    const int heads = g.kslice / 64, h0 = kbase / 64;
-    for (int i = warp; i < BT * heads; i += AD_WARPS) {
-      const int row = i / heads, hh = i - row * heads;
-      float ox = 0.f, oy = 0.f;
-      if (row < p.B && !(p.done && p.done[row])) {
-        const float* sp = p.attn_part + ((size_t)(row * p.H + h0 + hh) * p.n_split) * AD_PART;
-        const int L = p.kv_len[row];
-        const int ns = min(p.n_split, (L + AD_SPLIT - 1) / AD_SPLIT);
-        float M = -INFINITY;
-        for (int s = 0; s < ns; ++s) M = fmaxf(M, __ldcg(sp + s * AD_PART));
-        float Ls = 0.f;
-        for (int s = 0; s < ns; ++s) {
-          const float* q = sp + s * AD_PART;
-          const float ms = __ldcg(q);
-          if (ms == -INFINITY) continue;
-          const float c = exp2f(ms - M);
-          const float2 a = __ldcg(reinterpret_cast<const float2*>(q + 4 + 2 * lane));
-          Ls += __ldcg(q + 1) * c;
-          ox += a.x * c;
-          oy += a.y * c;
-        }
-        const float inv = Ls > 0.f ? 1.f / Ls : 0.f;
-        ox *= inv; oy *= inv;
-      }
-      *reinterpret_cast<uint32_t*>(xs + (size_t)row * xstride + (hh * 64 + 2 * lane) * 2) = pack_half2(ox, oy);
-    }
   } else {
     const int vec_per_row = g.kslice / 8;
     for (int i = tid; i < BT * vec_per_row; i += AD_THREADS) {
       const int row = i / vec_per_row, v = i - row * vec_per_row;
       const bool ok = row < p.B;
-      cp_async16(xs + (size_t)row * xstride + v * 16, ok ? (p.g16 + (size_t)row * g.K + kbase + v * 8) : p.g16, ok);
+      const __half* src = (XSRC == X_ATTN) ? p.att16 : p.g16;   // merged attention output / gated FFN activations
+      cp_async16(xs + (size_t)row * xstride + v * 16, ok ? (src + (size_t)row * g.K + kbase + v * 8) : src, ok);
     }
     cp_async_commit();
     cp_async_wait<0>();
@@ -505,11 +477,46 @@ M5_DEVINL void attn_phase(const ArDecodeParams& p, const ArLayerDev& lw, const C
       acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
       acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
     }
-    float* sp = p.attn_part + ((size_t)(it.b * p.H + it.h) * p.n_split + it.s) * AD_PART;
+    float* sp0 = p.attn_part + ((size_t)(it.b * p.H + it.h) * p.n_split) * AD_PART;
+    float* sp = sp0 + (size_t)it.s * AD_PART;
     if (lane == 0) { __stcg(sp, M); __stcg(sp + 1, l); }
     if (grp == 0) {
       __stcg(reinterpret_cast<float4*>(sp + 4 + sub * 8), make_float4(acc[0], acc[1], acc[2], acc[3]));
       __stcg(reinterpret_cast<float4*>(sp + 4 + sub * 8 + 4), make_float4(acc[4], acc[5], acc[6], acc[7]));
+    }
+    // the warp that completes the last split of this (utterance, head) merges all of them (in split order: deterministic)
+    // and writes the fp16 attention output row the WO projection stages; the others move on to their next item
+    const int ns = (L + AD_SPLIT - 1) / AD_SPLIT;
+    __threadfence();
+    __syncwarp();
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(p.attn_tickets + it.b * p.H + it.h, 1);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket == ns - 1) {
+      __threadfence();
+      if (lane == 0) p.attn_tickets[it.b * p.H + it.h] = 0;
+      // lanes 0 .. ns-1 fetch (m, l) of one split each, everybody gets the maximum and the scaled weights by shuffle
+      float ms = -INFINITY, ls = 0.f;
+      if (lane < ns) { ms = __ldcg(sp0 + (size_t)lane * AD_PART); ls = __ldcg(sp0 + (size_t)lane * AD_PART + 1); }
+      float Mx = ms;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) Mx = fmaxf(Mx, __shfl_xor_sync(0xffffffffu, Mx, o));
+      const float cw = (ms == -INFINITY) ? 0.f : exp2f(ms - Mx);
+      float Ls = 0.f, ox = 0.f, oy = 0.f;
+      for (int s2 = 0; s2 < ns; s2 += 4) {          // 4 splits' rows in flight per round
+        float2 a[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          a[e] = (s2 + e < ns) ? __ldcg(reinterpret_cast<const float2*>(sp0 + (size_t)(s2 + e) * AD_PART + 4 + 2 * lane)) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float c = __shfl_sync(0xffffffffu, cw, min(s2 + e, 31));
+          const float le = __shfl_sync(0xffffffffu, ls, min(s2 + e, 31));
+          if (s2 + e < ns) { Ls += le * c; ox += a[e].x * c; oy += a[e].y * c; }
+        }
+      }
+      const float inv = Ls > 0.f ? 1.f / Ls : 0.f;
+      *reinterpret_cast<uint32_t*>(p.att16 + (size_t)it.b * D + it.h * 64 + 2 * lane) = pack_half2(ox * inv, oy * inv);
     }
   }
 }

@@ -34,6 +34,8 @@ struct ArDecodeParams {
   float* logits = nullptr;   // [B, V]
   float* attn_part = nullptr;  // [B, H, n_split, 68] split-KV partials (m, l, -, -, acc[64])
   int n_split = 1;
+  int* attn_tickets = nullptr;  // [B * H] zero between steps: the last split of a (row, head) merges
+  __half* att16 = nullptr;      // [B, D] merged attention output (fp16, what the reference's SDPA returns)
   __half* kc = nullptr; __half* vc = nullptr;   // [layer][B][Wc][D] fp16
   float* scratch = nullptr;  // split-K partial tiles, ar_decode_scratch_floats()
   int* counters = nullptr;   // one ticket per row tile, zero between phases
