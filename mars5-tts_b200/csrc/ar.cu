@@ -385,7 +385,7 @@ int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int3
   size_t bytes = block_scratch_bytes(big, 0, D, ffmax) + (size_t)spk_rows * D * 4 + (size_t)B * D * 4 + (size_t)rows * D * 4 + cache_bytes +
                  noise_bytes + dump_bytes + (size_t)B * (max_len + 64) * 4 + (size_t)B * (3 * D + V + 4 * D + F) * 4 +
                  decode_attn_scratch_bytes(B, c.ar_heads, n_split) + (n_ids + n_codes * Q) * 4 + (size_t)(rows + spk_rows) * 64 + (size_t(32) << 20) +
-                 ar_decode_attn_floats(B, c.ar_heads, ar_decode_splits_for(Wc)) * 4 + (size_t)(4 * ctx->num_sms + 64) * 32 * 128 * 4;
+                 ar_decode_attn_floats(B, c.ar_heads, ar_decode_splits_for(Wc, 256)) * 4 + (size_t)(4 * ctx->num_sms + 64) * 32 * 128 * 4;
   M5_TRY(ar.reserve(bytes));
   ArPlan p;
   M5_TRY(ar_build_plan(ctx, ar, p, B, prompt_len, spk_len));
@@ -419,7 +419,8 @@ int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int3
   dp.x = st.x; dp.qkv = st.qkv32; dp.g16 = st.g16; dp.att16 = st.att16; dp.logits = st.logits; dp.kc = kc; dp.vc = vc;
   M5_TRY(ar_decode_plan(dp, ctx->num_sms));
   dp.g_out.W = w.output;
-  dp.n_split = ar_decode_splits_for(Wc);
+  dp.split_keys = ar_decode_split_keys(B, c.ar_heads, Wc, ctx->num_sms);
+  dp.n_split = ar_decode_splits_for(Wc, dp.split_keys);
   {
     std::vector<ArLayerDev> hl(L);
     for (int l = 0; l < L; ++l) hl[l] = {w.layers[l].attn_norm, w.layers[l].ffn_norm, w.layers[l].wqkv, w.layers[l].wo, w.layers[l].w13, w.layers[l].w2};

@@ -34,7 +34,6 @@ static constexpr int AD_UNROLL = 6;      // 32-column weight chunks in flight pe
 static constexpr int AD_KT = 32;         // keys per TMA tile
 static constexpr int AD_NST = 3;         // TMA stages per warp
 static constexpr int AD_STAGE_BYTES = 2 * AD_KT * 128;                      // K tile + V tile
-static constexpr int AD_SPLIT = 256;     // keys per attention work item
 static constexpr int AD_PART = 68;       // floats per split partial: m, l, pad, pad, acc[64] (16-byte aligned rows)
 static constexpr int AD_SMEM_KV = AD_WARPS * AD_NST * AD_STAGE_BYTES;        // 192 KB
 static constexpr int AD_SMEM = AD_SMEM_KV + 1024;                            // + mbarriers, tickets
@@ -278,10 +277,10 @@ M5_DEVINL bool attn_item(const ArDecodeParams& p, int layer, int idx, AttnItem& 
   it.s = r - it.h * p.n_split;
   if (p.done && p.done[it.b]) return false;
   const int L = p.kv_len[it.b];               // positions 0 .. L-2 are cached, L-1 is the token of this step
-  it.k0 = it.s * AD_SPLIT;
+  it.k0 = it.s * p.split_keys;
   if (it.k0 >= L) return false;
-  it.n_cache = min(AD_SPLIT, L - 1 - it.k0);
-  it.has_new = (L - 1 < it.k0 + AD_SPLIT) ? 1 : 0;
+  it.n_cache = min(p.split_keys, L - 1 - it.k0);
+  it.has_new = (L - 1 < it.k0 + p.split_keys) ? 1 : 0;
   it.row0 = (layer * p.B + it.b) * p.Wc + it.k0;
   return true;
 }
@@ -402,15 +401,19 @@ M5_DEVINL void attn_phase(const ArDecodeParams& p, const ArLayerDev& lw, const C
         for (int i = 0; i < 8; ++i) pa[i] = 0.f;
 #pragma unroll
         for (int u = 0; u < AD_KT / 4; ++u) {
-          const float pe = exp2f(sc[u] - mn);
-          ps += pe;
-          const uint4 vv = *reinterpret_cast<const uint4*>(sv + (u * 4 + grp) * 128 + sub * 16);
-          const __half2* vh = reinterpret_cast<const __half2*>(&vv);
+          // rows of the tile beyond the context hold whatever the arena held (possibly NaN / Inf bit patterns): they must be
+          // skipped, not multiplied by a zero weight
+          if (u * 4 + grp < kvalid) {
+            const float pe = exp2f(sc[u] - mn);
+            ps += pe;
+            const uint4 vv = *reinterpret_cast<const uint4*>(sv + (u * 4 + grp) * 128 + sub * 16);
+            const __half2* vh = reinterpret_cast<const __half2*>(&vv);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = __half22float2(vh[i]);
-            pa[2 * i] += pe * f.x;
-            pa[2 * i + 1] += pe * f.y;
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __half22float2(vh[i]);
+              pa[2 * i] += pe * f.x;
+              pa[2 * i + 1] += pe * f.y;
+            }
           }
         }
         l = l * c + ps;
@@ -479,14 +482,25 @@ M5_DEVINL void attn_phase(const ArDecodeParams& p, const ArLayerDev& lw, const C
     }
     float* sp0 = p.attn_part + ((size_t)(it.b * p.H + it.h) * p.n_split) * AD_PART;
     float* sp = sp0 + (size_t)it.s * AD_PART;
-    if (lane == 0) { __stcg(sp, M); __stcg(sp + 1, l); }
-    if (grp == 0) {
+    const bool single = (L + p.split_keys - 1) / p.split_keys == 1;
+    if (lane == 0 && !single) { __stcg(sp, M); __stcg(sp + 1, l); }
+    if (grp == 0 && !single) {
       __stcg(reinterpret_cast<float4*>(sp + 4 + sub * 8), make_float4(acc[0], acc[1], acc[2], acc[3]));
       __stcg(reinterpret_cast<float4*>(sp + 4 + sub * 8 + 4), make_float4(acc[4], acc[5], acc[6], acc[7]));
     }
     // the warp that completes the last split of this (utterance, head) merges all of them (in split order: deterministic)
     // and writes the fp16 attention output row the WO projection stages; the others move on to their next item
-    const int ns = (L + AD_SPLIT - 1) / AD_SPLIT;
+    const int ns = (L + p.split_keys - 1) / p.split_keys;
+    if (ns == 1) {
+      // the whole context of this (utterance, head) was one work item: normalise and write the fp16 output row directly
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      if (grp == 0) {
+        *reinterpret_cast<uint4*>(p.att16 + (size_t)it.b * D + it.h * 64 + sub * 8) =
+            make_uint4(pack_half2(acc[0] * inv, acc[1] * inv), pack_half2(acc[2] * inv, acc[3] * inv),
+                       pack_half2(acc[4] * inv, acc[5] * inv), pack_half2(acc[6] * inv, acc[7] * inv));
+      }
+      continue;
+    }
     __threadfence();
     __syncwarp();
     int ticket = 0;
@@ -655,7 +669,16 @@ int ar_decode_max_tiles(const ArDecodeParams& p) {
   for (const ArGemm* g : {&p.g_qkv, &p.g_wo, &p.g_w13, &p.g_w2, &p.g_out}) mx = std::max(mx, g->tiles);
   return mx;
 }
-int ar_decode_splits_for(int max_kv) { return (max_kv + AD_SPLIT - 1) / AD_SPLIT; }
+// Keys per attention work item: one item per warp and (utterance, head) when B * H alone keeps most warps busy (no split
+// partials, no merge); otherwise the context is cut so that about 0.7 * (warps of the grid) items exist, >= 256 keys each.
+int ar_decode_split_keys(int B, int H, int max_kv, int num_sms) {
+  const int warps = num_sms * AD_WARPS;
+  const int target = std::max(1, (int)(0.7 * warps) / std::max(1, B * H));
+  int keys = (max_kv + target - 1) / target;
+  keys = std::max(256, ((keys + AD_KT - 1) / AD_KT) * AD_KT);
+  return keys;
+}
+int ar_decode_splits_for(int max_kv, int split_keys) { return (max_kv + split_keys - 1) / split_keys; }
 size_t ar_decode_attn_floats(int B, int H, int n_split) { return (size_t)B * H * n_split * AD_PART; }
 
 typedef CUresult (*AdEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

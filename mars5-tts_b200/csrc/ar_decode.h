@@ -34,6 +34,7 @@ struct ArDecodeParams {
   float* logits = nullptr;   // [B, V]
   float* attn_part = nullptr;  // [B, H, n_split, 68] split-KV partials (m, l, -, -, acc[64])
   int n_split = 1;
+  int split_keys = 256;         // cached keys per attention work item (multiple of 32), ar_decode_split_keys()
   int* attn_tickets = nullptr;  // [B * H] zero between steps: the last split of a (row, head) merges
   __half* att16 = nullptr;      // [B, D] merged attention output (fp16, what the reference's SDPA returns)
   __half* kc = nullptr; __half* vc = nullptr;   // [layer][B][Wc][D] fp16
@@ -47,7 +48,8 @@ struct ArDecodeParams {
 int ar_decode_plan(ArDecodeParams& p, int num_sms);          // fills the ArGemm splits and ssq_tiles
 size_t ar_decode_scratch_floats(const ArDecodeParams& p);
 int ar_decode_max_tiles(const ArDecodeParams& p);
-int ar_decode_splits_for(int max_kv);
+int ar_decode_split_keys(int B, int H, int max_kv, int num_sms);
+int ar_decode_splits_for(int max_kv, int split_keys);
 size_t ar_decode_attn_floats(int B, int H, int n_split);
 int ar_decode_launch(const ArDecodeParams& p, int num_sms, cudaStream_t stream);   // memset(gbar) + cooperative launch
 
