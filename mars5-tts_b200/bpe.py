@@ -206,16 +206,18 @@ class RegexTokenizer(_Tokenizer):
     def __init__(self, pattern: Optional[str] = None):
         super().__init__()
         self.pattern = GPT4_SPLIT_PATTERN if pattern is None else pattern
+        self._ctor_pattern = self.pattern   # what the reference compiles ONCE in __init__ (regex.py:32-33)
         self._compiled = None
 
     def load(self, model_file):
+        # like the reference: Tokenizer.load (base.py:140-168) overwrites self.pattern with the model file's line but the
+        # regex compiled in the constructor keeps being used -- the split pattern of a loaded model never takes effect
         super().load(model_file)
-        self._compiled = None
 
     @property
     def compiled_pattern(self):
         if self._compiled is None:
-            self._compiled = _regex().compile(self.pattern)
+            self._compiled = _regex().compile(self._ctor_pattern)
         return self._compiled
 
     # -> for every text a list of segments: an int (special id) or a list of chunk byte strings

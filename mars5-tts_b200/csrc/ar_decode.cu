@@ -6,8 +6,9 @@
 // barrier (5 per layer):
 //   P0        x = embed(last token) (+ per-row sum-of-squares partials)
 //   per layer:
-//     P1  QKV projection      X = fp16(RMSNorm(x) * gamma) staged per CTA, weights streamed once (ld.global.nc, 128-bit)
-//                             into mma.sync fragments, split-K partials, last CTA of a row tile reduces -> qkv fp32
+//     P1  QKV projection      X = fp16(RMSNorm(x) * gamma) staged per CTA, weights streamed once through a 16-deep per-warp
+//                             cp.async ring (128 KB in flight per SM) into mma.sync fragments, split-K partials, last CTA of
+//                             a row tile reduces -> qkv fp32
 //     P2  attention           one (utterance, head, 256-key split) per WARP: q / new k get RoPE from the fp32 qkv row, the new
 //                             k, v are appended to the fp16 KV cache, the cached keys / values arrive as 32-key TMA tiles
 //                             (cp.async.bulk.tensor, 3-deep per-warp mbarrier ring in shared memory), online softmax in
@@ -30,12 +31,15 @@ namespace m5 {
 
 static constexpr int AD_THREADS = 256, AD_WARPS = 8;
 static constexpr int AD_ROWS = 128;      // weight rows per GEMM work item (16 per warp)
-static constexpr int AD_UNROLL = 6;      // 32-column weight chunks in flight per warp
+static constexpr int AD_WST = 16;        // 32-column weight chunks (1 KB each) a warp keeps in flight through cp.async
+static constexpr int AD_W_BYTES = AD_WARPS * AD_WST * 1024;                  // weight staging: 128 KB, [warp][slot][2][lane][16 B]
 static constexpr int AD_KT = 32;         // keys per TMA tile
 static constexpr int AD_NST = 3;         // TMA stages per warp
 static constexpr int AD_STAGE_BYTES = 2 * AD_KT * 128;                      // K tile + V tile
 static constexpr int AD_PART = 68;       // floats per split partial: m, l, pad, pad, acc[64] (16-byte aligned rows)
-static constexpr int AD_SMEM_KV = AD_WARPS * AD_NST * AD_STAGE_BYTES;        // 192 KB
+static constexpr int AD_SMEM_KV = AD_WARPS * AD_NST * AD_STAGE_BYTES;        // 192 KB (the GEMM phases alias it: W staging + X)
+static constexpr int AD_MAX_KSLICE = 896;                                    // activation slice: 32 rows x (2 * 896 + 64) B = 58 KB
+static_assert(AD_W_BYTES + 32 * (AD_MAX_KSLICE * 2 + 64) <= AD_SMEM_KV, "weight staging + activation slice must fit the KV ring region");
 static constexpr int AD_SMEM = AD_SMEM_KV + 1024;                            // + mbarriers, tickets
 
 M5_DEVINL uint4 ad_ldg_stream(const void* p) {
@@ -75,8 +79,6 @@ M5_DEVINL void grid_sync(unsigned* bar, unsigned& epoch, unsigned long long* pro
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM phases
-struct WFrag { uint4 a[AD_UNROLL], b[AD_UNROLL]; };
-
 // item -> (row tile, K slice); rows of W this lane streams
 struct GemmItem {
   int tile, ks, n0, kbase;
@@ -93,14 +95,21 @@ M5_DEVINL GemmItem gemm_item(const ArGemm& g, int item, int warp, int lane) {
   it.w1 = g.W + (size_t)r1 * g.K + it.kbase + 8 * t;
   return it;
 }
-M5_DEVINL void gemm_fetch(const ArGemm& g, const GemmItem& it, int c0, WFrag& f) {
+// Weight streaming: every lane copies ITS OWN two 16-byte fragment pieces of chunk c (rows n0+g and n0+g+8, columns
+// 32c + 8t ..) with cp.async.cg into a lane-private slot of shared memory, one commit group per chunk.  AD_WST chunks
+// (16 KB per warp, 128 KB per SM) are in flight -- more than registers could hold -- and the first ones are requested
+// before the preceding grid barrier.
+M5_DEVINL void w_issue(const GemmItem& it, uint8_t* wst, int lane, int c) {
+  uint8_t* dst = wst + (c & (AD_WST - 1)) * 1024 + lane * 16;
+  cp_async16(dst, it.w0 + c * 32, true);
+  cp_async16(dst + 512, it.w1 + c * 32, true);
+}
+M5_DEVINL void w_prologue(const ArGemm& g, const GemmItem& it, uint8_t* wst, int lane) {
   const int chunks = g.kslice / 32;
 #pragma unroll
-  for (int u = 0; u < AD_UNROLL; ++u) {
-    if (c0 + u < chunks) {
-      f.a[u] = ad_ldg_stream(it.w0 + (c0 + u) * 32);
-      f.b[u] = ad_ldg_stream(it.w1 + (c0 + u) * 32);
-    }
+  for (int u = 0; u < AD_WST; ++u) {
+    if (u < chunks) w_issue(it, wst, lane, u);
+    cp_async_commit();   // (possibly empty) group u: the wait_group arithmetic below stays uniform
   }
 }
 
@@ -153,11 +162,12 @@ M5_DEVINL void stage_x(const ArDecodeParams& p, const ArGemm& g, int kbase, cons
 // first item when `have_pre` (requested before the preceding grid barrier).
 template <int NT, int XSRC, int EPI>
 M5_DEVINL void gemm_phase(const ArDecodeParams& p, const ArGemm& g, const float* gamma, float* out_f32, int ldo, uint8_t* smem,
-                          WFrag& pre, bool have_pre) {
+                          bool have_pre) {
   constexpr int BT = 8 * NT;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gq = lane >> 2, t = lane & 3;
-  uint8_t* xs = smem;
+  uint8_t* wst = smem + warp * (AD_WST * 1024);                          // this warp's weight slots
+  uint8_t* xs = smem + AD_W_BYTES;                                        // activation slice of the item
   float* s_scale = reinterpret_cast<float*>(smem + AD_SMEM_KV + 512);   // [32]
   int* s_ticket = reinterpret_cast<int*>(smem + AD_SMEM_KV + 512 + 128);
   const int n_items = g.tiles * g.ksplit;
@@ -165,34 +175,30 @@ M5_DEVINL void gemm_phase(const ArDecodeParams& p, const ArGemm& g, const float*
   const int xstride = g.kslice * 2 + 64;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const GemmItem it = gemm_item(g, item, warp, lane);
-    if (!have_pre) gemm_fetch(g, it, 0, pre);
+    if (!have_pre) w_prologue(g, it, wst, lane);
     have_pre = false;
     stage_x<NT, XSRC>(p, g, it.kbase, gamma, xs, s_scale);
     float acc[NT][4];
 #pragma unroll
     for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-    // rolling prefetch: slot u always holds chunk c0 + u; as soon as its two MMAs per batch tile are issued the slot is
-    // refilled with chunk c0 + u + AD_UNROLL, so AD_UNROLL chunks (12 x 16 B per lane) stay in flight for the whole slice
-    for (int c0 = 0; c0 < chunks; c0 += AD_UNROLL) {
+    // chunk c is the (c+1)-th oldest commit group still tracked: all but the newest AD_WST - 1 groups have landed
+#pragma unroll 4
+    for (int c = 0; c < chunks; ++c) {
+      cp_async_wait<AD_WST - 1>();
+      const uint8_t* src = wst + (c & (AD_WST - 1)) * 1024 + lane * 16;
+      const uint4 wa = *reinterpret_cast<const uint4*>(src), wb = *reinterpret_cast<const uint4*>(src + 512);
+      if (c + AD_WST < chunks) w_issue(it, wst, lane, c + AD_WST);   // refill the slot just read (lane-private data)
+      cp_async_commit();
+      const uint32_t a1[4] = {wa.x, wb.x, wa.y, wb.y};
+      const uint32_t a2[4] = {wa.z, wb.z, wa.w, wb.w};
 #pragma unroll
-      for (int u = 0; u < AD_UNROLL; ++u) {
-        const int c = c0 + u;
-        if (c < chunks) {
-          const uint32_t a1[4] = {pre.a[u].x, pre.b[u].x, pre.a[u].y, pre.b[u].y};
-          const uint32_t a2[4] = {pre.a[u].z, pre.b[u].z, pre.a[u].w, pre.b[u].w};
-          if (c + AD_UNROLL < chunks) {
-            pre.a[u] = ad_ldg_stream(it.w0 + (c + AD_UNROLL) * 32);
-            pre.b[u] = ad_ldg_stream(it.w1 + (c + AD_UNROLL) * 32);
-          }
-#pragma unroll
-          for (int nt = 0; nt < NT; ++nt) {
-            const uint4 x = *reinterpret_cast<const uint4*>(xs + (size_t)(nt * 8 + gq) * xstride + (c * 32 + 8 * t) * 2);
-            mma_16816(acc[nt], a1, x.x, x.y);
-            mma_16816(acc[nt], a2, x.z, x.w);
-          }
-        }
+      for (int nt = 0; nt < NT; ++nt) {
+        const uint4 x = *reinterpret_cast<const uint4*>(xs + (size_t)(nt * 8 + gq) * xstride + (c * 32 + 8 * t) * 2);
+        mma_16816(acc[nt], a1, x.x, x.y);
+        mma_16816(acc[nt], a2, x.z, x.w);
       }
     }
+    cp_async_wait<0>();
     // ---- partial tile -> scratch[item][b][row]
     float* part = p.scratch + (size_t)item * (32 * AD_ROWS);
     const int rl = warp * 16 + gq;
@@ -554,7 +560,7 @@ ar_decode_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_consta
   AttnWarpState ast;
   ast.issued = ast.consumed = 0;
   ast.prod.valid = false;
-  WFrag wf;
+  uint8_t* wst = smem + warp * (AD_WST * 1024);
 
   // ---- P0: x = embed[last token] (nn.Embedding is not autocast: fp32 value of the fp16-exact weight) + sums of squares
   {
@@ -577,7 +583,7 @@ ar_decode_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_consta
   {
     const ArLayerDev& l0 = p.layers[0];
     ArGemm g = p.g_qkv; g.W = l0.wqkv;
-    if ((int)blockIdx.x < g.tiles * g.ksplit) gemm_fetch(g, gemm_item(g, blockIdx.x, warp, lane), 0, wf);
+    if ((int)blockIdx.x < g.tiles * g.ksplit) w_prologue(g, gemm_item(g, blockIdx.x, warp, lane), wst, lane);
   }
   unsigned long long* pf = p.prof;   // advances by 2 stamps per barrier
   grid_sync(p.gbar, epoch, pf);
@@ -588,42 +594,43 @@ ar_decode_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_consta
     ArGemm g;
     // ---- P1: qkv = Wqkv . rmsnorm(x)
     g = p.g_qkv; g.W = lw.wqkv;
-    gemm_phase<NT, X_NORM, EPI_STORE>(p, g, lw.attn_norm, p.qkv, 3 * p.D, smem, wf, (int)blockIdx.x < g.tiles * g.ksplit);
+    gemm_phase<NT, X_NORM, EPI_STORE>(p, g, lw.attn_norm, p.qkv, 3 * p.D, smem, (int)blockIdx.x < g.tiles * g.ksplit);
     __syncthreads();
     attn_prefetch(p, &tmap_k, &tmap_v, layer, ring, bars, ast);
     grid_sync(p.gbar, epoch, pf);
     if (pf) pf += 2;
     // ---- P2: attention over the cache + the new token
     attn_phase(p, lw, &tmap_k, &tmap_v, layer, ring, bars, ast);
+    __syncthreads();   // the weight slots alias OTHER warps' KV rings: every warp of the CTA must be through with its tiles
     g = p.g_wo; g.W = lw.wo;
     const bool pre_wo = (int)blockIdx.x < g.tiles * g.ksplit;
-    if (pre_wo) gemm_fetch(g, gemm_item(g, blockIdx.x, warp, lane), 0, wf);
+    if (pre_wo) w_prologue(g, gemm_item(g, blockIdx.x, warp, lane), wst, lane);
     grid_sync(p.gbar, epoch, pf);
     if (pf) pf += 2;
     // ---- P3: x += Wo . attn
-    gemm_phase<NT, X_ATTN, EPI_RESID>(p, g, nullptr, p.x, p.D, smem, wf, pre_wo);
+    gemm_phase<NT, X_ATTN, EPI_RESID>(p, g, nullptr, p.x, p.D, smem, pre_wo);
     g = p.g_w13; g.W = lw.w13;
     const bool pre_13 = (int)blockIdx.x < g.tiles * g.ksplit;
-    if (pre_13) gemm_fetch(g, gemm_item(g, blockIdx.x, warp, lane), 0, wf);
+    if (pre_13) w_prologue(g, gemm_item(g, blockIdx.x, warp, lane), wst, lane);
     grid_sync(p.gbar, epoch, pf);
     if (pf) pf += 2;
     // ---- P4: g = silu(W1 . h) * (W3 . h), h = rmsnorm(x)
-    gemm_phase<NT, X_NORM, EPI_SWIGLU>(p, g, lw.ffn_norm, nullptr, 0, smem, wf, pre_13);
+    gemm_phase<NT, X_NORM, EPI_SWIGLU>(p, g, lw.ffn_norm, nullptr, 0, smem, pre_13);
     g = p.g_w2; g.W = lw.w2;
     const bool pre_2 = (int)blockIdx.x < g.tiles * g.ksplit;
-    if (pre_2) gemm_fetch(g, gemm_item(g, blockIdx.x, warp, lane), 0, wf);
+    if (pre_2) w_prologue(g, gemm_item(g, blockIdx.x, warp, lane), wst, lane);
     grid_sync(p.gbar, epoch, pf);
     if (pf) pf += 2;
     // ---- P5: x += W2 . g
-    gemm_phase<NT, X_F16, EPI_RESID>(p, g, nullptr, p.x, p.D, smem, wf, pre_2);
+    gemm_phase<NT, X_F16, EPI_RESID>(p, g, nullptr, p.x, p.D, smem, pre_2);
     if (layer + 1 < p.n_layers) { g = p.g_qkv; g.W = p.layers[layer + 1].wqkv; }
     else { g = p.g_out; }
-    if ((int)blockIdx.x < g.tiles * g.ksplit) gemm_fetch(g, gemm_item(g, blockIdx.x, warp, lane), 0, wf);
+    if ((int)blockIdx.x < g.tiles * g.ksplit) w_prologue(g, gemm_item(g, blockIdx.x, warp, lane), wst, lane);
     grid_sync(p.gbar, epoch, pf);
     if (pf) pf += 2;
   }
   // ---- logits = Wout . rmsnorm(x)
-  gemm_phase<NT, X_NORM, EPI_STORE>(p, p.g_out, p.final_norm, p.logits, p.V, smem, wf, (int)blockIdx.x < p.g_out.tiles * p.g_out.ksplit);
+  gemm_phase<NT, X_NORM, EPI_STORE>(p, p.g_out, p.final_norm, p.logits, p.V, smem, (int)blockIdx.x < p.g_out.tiles * p.g_out.ksplit);
   if (pf && blockIdx.x == 0 && tid == 0) pf[0] = pf[1] = global_timer_ns();
 }
 
@@ -636,14 +643,14 @@ static void pick(ArGemm& g, int N, int K, int grid) {
   for (int s = 1; s <= kb && s <= 16; ++s) {
     if (kb % s) continue;
     const int ksl = K / s;
-    if (ksl < 128 || ksl > 1024) continue;
+    if (ksl < 128 || ksl > AD_MAX_KSLICE) continue;
     const int items = g.tiles * s;
     // SM utilisation of the phase minus a price per extra K slice (partial-sum traffic, one staging + ticket per item)
     const double u = (double)items / ((double)((items + grid - 1) / grid) * grid) - 0.02 * s;
     if (u > best_u) { best_u = u; best = s; }
   }
   if (best_u < -1e8) {   // K too small / too large for the limits above: smallest admissible split
-    for (int s = 1; s <= kb; ++s) if (kb % s == 0 && K / s <= 1024) { best = s; break; }
+    for (int s = 1; s <= kb; ++s) if (kb % s == 0 && K / s <= AD_MAX_KSLICE) { best = s; break; }
   }
   g.ksplit = best; g.kslice = K / best;
 }

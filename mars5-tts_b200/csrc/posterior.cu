@@ -30,7 +30,8 @@ __device__ __forceinline__ float gumbel_from_u(float u) {
 }
 __device__ __forceinline__ void uniforms4(uint64_t seed, uint64_t utt, uint32_t pos, uint32_t tag, uint32_t grp, float out[4]) {
   uint32_t o[4];
-  philox4x32((uint32_t)seed ^ (uint32_t)utt, (uint32_t)(seed >> 32) ^ (uint32_t)(utt >> 32), grp, tag, pos, 0x4d415253u, o);
+  // key = seed, counter = (group, tag, position, utterance): (seed 1, utt 0) and (seed 0, utt 1) are different streams
+  philox4x32((uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x4d415253u, grp, tag, pos, (uint32_t)utt ^ ((uint32_t)(utt >> 32) * 0x9E3779B9u), o);
 #pragma unroll
   for (int i = 0; i < 4; ++i) out[i] = (o[i] >> 8) * (1.0f / 16777216.0f);  // [0,1) like torch.rand
 }

@@ -109,6 +109,13 @@ class Engine:
     def _mem(x):
         return capi.MEM_DEVICE if torch.is_tensor(x) and x.is_cuda else capi.MEM_HOST
 
+    def _fence(self, mem):
+        """Device buffers (inputs made by the caller, outputs zero-filled below) are produced on torch's current stream but
+        consumed on the context's own stream: drain torch's stream first.  Every C-ABI call returns after ITS stream has
+        drained, so results are safe to read from torch afterwards."""
+        if mem == capi.MEM_DEVICE:
+            torch.cuda.current_stream(torch.device("cuda", self.device)).synchronize()
+
     def _alloc(self, mem, shape, dtype):
         if mem == capi.MEM_DEVICE:
             return torch.zeros(shape, dtype={np.int32: torch.int32, np.float32: torch.float32}[dtype],
@@ -138,6 +145,7 @@ class Engine:
         out_len, hit = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
         nsteps = 0 if noise is None else noise.shape[1]
         dump = self._alloc(mem, (B, dump_steps, V), np.float32) if dump_steps else None
+        self._fence(mem)
         rc = self.lib.m5_ar_generate(self.ctx, B, capi.ptr(ids), capi.ptr(plen_a), capi.ptr(codes), capi.ptr(slen_a),
                                      capi.ptr(nph_a), C.byref(ar_cfg), mem, capi.ptr(noise), nsteps, C.c_uint64(seed),
                                      capi.ptr(utt_a), capi.ptr(out_ids), capi.ptr(out_len), capi.ptr(hit), capi.ptr(dump),
@@ -188,6 +196,7 @@ class Engine:
         tlen_a, clen_a, xlen_a = _i32(tlen), _i32(clen), _i32(xlen)
         utt_a = np.ascontiguousarray(np.asarray(utt, dtype=np.int64)) if utt is not None else None
         out = self._alloc(mem, (int(np.sum(xlen)), 8), np.int32)
+        self._fence(mem)
         rc = self.lib.m5_nar_infer(self.ctx, B, capi.ptr(text), capi.ptr(tlen_a), capi.ptr(codes), capi.ptr(clen_a),
                                    capi.ptr(l0), capi.ptr(xlen_a), C.byref(nar_cfg), mem, capi.ptr(x_init), capi.ptr(noise),
                                    C.c_uint64(seed), capi.ptr(utt_a), capi.ptr(out))
@@ -221,6 +230,7 @@ class Engine:
     def vocode_packed(self, codes, n_frames, bandwidth_id=1):
         mem, nf_a = self._mem(codes), _i32(n_frames)
         out = self._alloc(mem, (int(np.sum(n_frames)) * self.dims["voc_hop"],), np.float32)
+        self._fence(mem)
         rc = self.lib.m5_vocode(self.ctx, len(n_frames), capi.ptr(codes), capi.ptr(nf_a), int(bandwidth_id), mem, capi.ptr(out))
         capi.check(self.ctx, rc, "m5_vocode")
         return out
