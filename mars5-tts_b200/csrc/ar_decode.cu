@@ -226,10 +226,14 @@ M5_DEVINL void gemm_phase(const ArDecodeParams& p, const ArGemm& g, const float*
         const int n = nrow0 + 2 * pr;
         if (b >= p.B || n + 1 >= g.N) continue;
         float a = 0.f, c = 0.f;
-        for (int s = 0; s < g.ksplit; ++s) {
-          const float2 v2 = __ldcg(reinterpret_cast<const float2*>(base + (size_t)s * (32 * AD_ROWS) + (size_t)b * AD_ROWS + 2 * pr));
-          a += v2.x;
-          c += v2.y;
+        for (int s0 = 0; s0 < g.ksplit; s0 += 4) {   // 4 slices' loads in flight, summed in slice order (deterministic)
+          float2 v2[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            v2[e] = (s0 + e < g.ksplit) ? __ldcg(reinterpret_cast<const float2*>(base + (size_t)(s0 + e) * (32 * AD_ROWS) + (size_t)b * AD_ROWS + 2 * pr))
+                                        : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { a += v2[e].x; c += v2[e].y; }
         }
         p.g16[(size_t)b * (g.N / 2) + (n >> 1)] = __float2half_rn((a / (1.f + __expf(-a))) * c);
       }
@@ -237,17 +241,27 @@ M5_DEVINL void gemm_phase(const ArDecodeParams& p, const ArGemm& g, const float*
       // warp w owns batch rows w, w + 8, ...; a lane owns 4 consecutive weight rows (= output columns) of the tile
       for (int b = warp; b < BT; b += AD_WARPS) {
         if (b >= p.B) continue;
+        float4 r_pre = make_float4(0.f, 0.f, 0.f, 0.f);   // residual row segment, requested before the partial sums
+        if constexpr (EPI == EPI_RESID) {
+          if (nrow0 + 4 * lane + 3 < g.N && (ldo & 3) == 0)
+            r_pre = __ldcg(reinterpret_cast<const float4*>(out_f32 + (size_t)b * ldo + nrow0 + 4 * lane));
+        }
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < g.ksplit; ++s) {
-          const float4 q = __ldcg(reinterpret_cast<const float4*>(base + (size_t)s * (32 * AD_ROWS) + (size_t)b * AD_ROWS + 4 * lane));
-          v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+        for (int s0 = 0; s0 < g.ksplit; s0 += 4) {   // 4 slices' loads in flight, summed in slice order (deterministic)
+          float4 q[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            q[e] = (s0 + e < g.ksplit) ? __ldcg(reinterpret_cast<const float4*>(base + (size_t)(s0 + e) * (32 * AD_ROWS) + (size_t)b * AD_ROWS + 4 * lane))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { v.x += q[e].x; v.y += q[e].y; v.z += q[e].z; v.w += q[e].w; }
         }
         const int n = nrow0 + 4 * lane;
         float* o = out_f32 + (size_t)b * ldo + n;
         float sq = 0.f;
         if (n + 3 < g.N && (ldo & 3) == 0) {
           if constexpr (EPI == EPI_RESID) {
-            const float4 r = __ldcg(reinterpret_cast<const float4*>(o));
+            const float4 r = r_pre;
             v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
             sq = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
           }

@@ -323,3 +323,25 @@ def test_ar_generate_rejects_more_than_32_rows(tiny):
     acfg = eng.make_ar_cfg(InferenceConfig(), 40, inp["eos"])
     with pytest.raises(capi.M5Error, match="at most 32"):
         eng.ar_generate([inp["ar_prompt"].tolist()] * 33, [inp["ar_spk"].numpy()] * 33, [7] * 33, acfg)
+
+
+def test_ar_decode_long_context_split_merge(tiny):
+    """Contexts longer than one 256-key attention work item: the fused decode kernel cuts the cache into splits, one warp
+    each, and the warp finishing the last split merges them (ticket).  Logits of the first decode steps against the
+    oracle's full forward, two rows of different length in one batch, and batch == solo (deterministic merge order)."""
+    inp, ar_sd, _, _, eng, cfg = tiny
+    g = torch.Generator().manual_seed(61)
+    prompts = [torch.randint(258, 1282, (n,), generator=g).tolist() for n in (300, 530)]
+    spks = [torch.randint(0, 1024, (n, 8), generator=g).numpy() for n in (12, 5)]
+    acfg = eng.make_ar_cfg(InferenceConfig(temperature=1.0, top_k=50, top_p=0.95), 540, inp["eos"], sync_every=2)
+    noise = torch.empty(2, 4, inp["V"]).exponential_(1, generator=g)
+    ids, _, dump = eng.ar_generate(prompts, spks, [50, 50], acfg, noise=noise.numpy(), dump_steps=3)
+    for b in range(2):
+        P = len(prompts[b])
+        assert len(ids[b]) >= P + 3
+        for s in range(3):
+            ref = ar_oracle.codeclm_forward(ar_sd, cfg, torch.from_numpy(ids[b][:P + s].astype(np.int64)), torch.from_numpy(spks[b]))[-1].numpy()
+            err = np.abs(dump[b, s] - ref).max()
+            assert err < logit_tol(ref), (b, s, err)
+        solo, _, _ = eng.ar_generate([prompts[b]], [spks[b]], [50], acfg, noise=noise[b:b + 1].numpy())
+        np.testing.assert_array_equal(ids[b], solo[0])
