@@ -11,8 +11,8 @@
 //                             a row tile reduces -> qkv fp32
 //     P2  attention           one (utterance, head, 256-key split) per WARP: q / new k get RoPE from the fp32 qkv row, the new
 //                             k, v are appended to the fp16 KV cache, the cached keys / values arrive as 32-key TMA tiles
-//                             (cp.async.bulk.tensor, 3-deep per-warp mbarrier ring in shared memory), online softmax in
-//                             fp32, per-split (m, l, acc) partials
+//                             (cp.async.bulk.tensor, 4-deep per-warp mbarrier ring in shared memory, 6 attention warps per
+//                             CTA), blocked online softmax in fp32; per-split (m, l, acc) partials only when the context is cut
 //     P3  WO projection       X = merged attention output (split partials merged while staging); epilogue x += ...,
 //                             and the row sums of squares the next RMSNorm needs (per 128-column tile, fixed order)
 //     P4  W1|W3 + SwiGLU      X = fp16(RMSNorm(x) * gamma); epilogue silu(w1 x) * (w3 x) -> g fp16
@@ -34,10 +34,11 @@ static constexpr int AD_ROWS = 128;      // weight rows per GEMM work item (16 p
 static constexpr int AD_WST = 16;        // 32-column weight chunks (1 KB each) a warp keeps in flight through cp.async
 static constexpr int AD_W_BYTES = AD_WARPS * AD_WST * 1024;                  // weight staging: 128 KB, [warp][slot][2][lane][16 B]
 static constexpr int AD_KT = 32;         // keys per TMA tile
-static constexpr int AD_NST = 3;         // TMA stages per warp
+static constexpr int AD_NST = 4;         // TMA stages per attention warp (3 tiles = 24 KB in flight while one is consumed)
+static constexpr int AD_AWARPS = 6;      // warps of a CTA that run attention items: 6 x 4 stages x 8 KB = the 192 KB ring
 static constexpr int AD_STAGE_BYTES = 2 * AD_KT * 128;                      // K tile + V tile
 static constexpr int AD_PART = 68;       // floats per split partial: m, l, pad, pad, acc[64] (16-byte aligned rows)
-static constexpr int AD_SMEM_KV = AD_WARPS * AD_NST * AD_STAGE_BYTES;        // 192 KB (the GEMM phases alias it: W staging + X)
+static constexpr int AD_SMEM_KV = AD_AWARPS * AD_NST * AD_STAGE_BYTES;       // 192 KB (the GEMM phases alias it: W staging + X)
 static constexpr int AD_MAX_KSLICE = 896;                                    // activation slice: 32 rows x (2 * 896 + 64) B = 58 KB
 static_assert(AD_W_BYTES + 32 * (AD_MAX_KSLICE * 2 + 64) <= AD_SMEM_KV, "weight staging + activation slice must fit the KV ring region");
 static constexpr int AD_SMEM = AD_SMEM_KV + 1024;                            // + mbarriers, tickets
@@ -340,8 +341,9 @@ struct AttnWarpState {
 
 M5_DEVINL void attn_prefetch(const ArDecodeParams& p, const CUtensorMap* tk, const CUtensorMap* tv, int layer, uint8_t* ring,
                              uint64_t* bars, AttnWarpState& st) {
-  const int lane = threadIdx.x & 31, gw = blockIdx.x * AD_WARPS + (threadIdx.x >> 5);
-  const int total = p.B * p.H * p.n_split, stride = gridDim.x * AD_WARPS;
+  if ((threadIdx.x >> 5) >= AD_AWARPS) return;
+  const int lane = threadIdx.x & 31, gw = blockIdx.x * AD_AWARPS + (threadIdx.x >> 5);
+  const int total = p.B * p.H * p.n_split, stride = gridDim.x * AD_AWARPS;
   st.prod.idx = gw;
   tile_seek(p, layer, total, stride, st.prod);
   while (st.prod.valid && st.issued - st.consumed < AD_NST) {
@@ -353,9 +355,10 @@ M5_DEVINL void attn_prefetch(const ArDecodeParams& p, const CUtensorMap* tk, con
 
 M5_DEVINL void attn_phase(const ArDecodeParams& p, const ArLayerDev& lw, const CUtensorMap* tk, const CUtensorMap* tv, int layer,
                           uint8_t* ring, uint64_t* bars, AttnWarpState& st) {
-  const int lane = threadIdx.x & 31, gw = blockIdx.x * AD_WARPS + (threadIdx.x >> 5);
+  if ((threadIdx.x >> 5) >= AD_AWARPS) return;   // warps 6, 7 own no KV ring: they wait at the CTA barrier that follows
+  const int lane = threadIdx.x & 31, gw = blockIdx.x * AD_AWARPS + (threadIdx.x >> 5);
   const int sub = lane & 7, grp = lane >> 3;
-  const int total = p.B * p.H * p.n_split, stride = gridDim.x * AD_WARPS;
+  const int total = p.B * p.H * p.n_split, stride = gridDim.x * AD_AWARPS;
   const int D = p.D;
   const float sl2 = 0.125f * 1.4426950408889634f;
   (void)lw;
@@ -563,8 +566,8 @@ ar_decode_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_consta
   uint8_t* smem = ad_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AD_SMEM_KV) + warp * AD_NST;   // this warp's stage barriers
-  uint8_t* ring = smem + warp * (AD_NST * AD_STAGE_BYTES);
-  if (lane == 0) {
+  uint8_t* ring = smem + (warp < AD_AWARPS ? warp : 0) * (AD_NST * AD_STAGE_BYTES);
+  if (lane == 0 && warp < AD_AWARPS) {
     for (int s = 0; s < AD_NST; ++s) mbar_init(bars + s, 1);
     fence_barrier_init();
   }
@@ -693,7 +696,7 @@ int ar_decode_max_tiles(const ArDecodeParams& p) {
 // Keys per attention work item: one item per warp and (utterance, head) when B * H alone keeps most warps busy (no split
 // partials, no merge); otherwise the context is cut so that about 0.7 * (warps of the grid) items exist, >= 256 keys each.
 int ar_decode_split_keys(int B, int H, int max_kv, int num_sms) {
-  const int warps = num_sms * AD_WARPS;
+  const int warps = num_sms * AD_AWARPS;
   const int target = std::max(1, (int)(0.7 * warps) / std::max(1, B * H));
   int keys = (max_kv + target - 1) / target;
   keys = std::max(256, ((keys + AD_KT - 1) / AD_KT) * AD_KT);
