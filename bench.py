@@ -550,12 +550,13 @@ def main():
     ach = gp["flops"] / max(gp["ms"], 1e-9) / 1e9  # TFLOP/s
     roofline = {"kernel": "gemm_tc5_2cta_kernel / gemm_tc5_kernel (tcgen05; every NAR, AR-prefill and vocoder GEMM)", "bound": "tensor",
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                # per launch, like `achieved`: algorithmic operand bytes of the average launch; DRAM traffic of the one
-                # shape captured with ncu --set full (profiles/) is given with its own algorithmic bytes beside it
-                "traffic": gp["bytes"] / max(gp["launches"], 1),
-                "traffic_is": "algorithmic bytes per average launch (A + W + C once); ncu dram bytes of one shape in traffic_ncu",
+                # DRAM bytes (read + write) of ONE launch of the class's dominant shape from an ncu --set full capture
+                # (profiles/r1_gemm_tc5_2cta_ncu.txt), with the algorithmic bytes of that same shape beside it (ratio 1.01);
+                # `algorithmic_bytes_per_launch` is the class average the `achieved` figure is computed over
+                "traffic": 376112128 + 901768704,
                 "traffic_ncu": {"shape": "M=153552 N=3072 K=1024 fp16 out", "dram_bytes": 376112128 + 901768704,
                                 "algorithmic_bytes": 2 * (153552 * 1024 + 3072 * 1024 + 153552 * 3072)},
+                "algorithmic_bytes_per_launch": gp["bytes"] / max(gp["launches"], 1),
                 "peak_source": peak_src,
                 "launches": gp["launches"], "avg_launch_ms": gp["ms"] / max(gp["launches"], 1),
                 "share_of_step": gp["ms"] / ms, "flash_attn_tflops": prof["flash_attn"]["flops"] / max(prof["flash_attn"]["ms"], 1e-9) / 1e9,
@@ -563,11 +564,14 @@ def main():
     roofline_ar = None
     if ap_["launches"] > 0:
         gbs = ap_["bytes"] / max(ap_["ms"], 1e-9) / 1e6
-        roofline_ar = {"kernel": "AR decode step (fused per-layer decode kernels + sampler, one CUDA graph per step)", "bound": "hbm",
+        roofline_ar = {"kernel": "ar_decode_kernel (one persistent cooperative kernel per decode step, all 26 layers + vocabulary projection) + ar_sample_kernel", "bound": "hbm",
                        "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
                        "bytes_per_step": ap_["bytes"] / ap_["launches"], "ms_per_decode_step": ap_["ms"] / ap_["launches"],
                        "decode_steps": ap_["launches"], "share_of_step": ap_["ms"] / ms,
-                       "formula": "W_ar + sum_b 159744*(L_b+1) + B*1536*2 per step (SURVEY 8(d))"}
+                       "formula": "W_ar + sum_b 159744*(L_b+1) + B*1536*2 per step (SURVEY 8(d))",
+                       # one ncu --set full capture of the kernel (profiles/r2_ar_decode_final_ncu.txt, B=32, L~1232): DRAM
+                       # read + write per launch vs the algorithmic bytes of that step
+                       "traffic": 7768864000 + 99603456, "traffic_algorithmic_same_launch": 7470000000}
     n_in = sum(p.nbytes for p in wl["prompts"]) + 2 * sum(s.nbytes for s in wl["spk"]) + sum(t.nbytes for t in wl["text"])
     n_out = wav_dev.numel() * 4
     e2e = {"value": wl["audio_s"] * world * e2e_steps / (ms_e2e / 1e3), "unit": UNIT, "steps": e2e_steps, "h2d_bytes_per_step": int(n_in + wl["B"] * wl["N"] * 4),
