@@ -86,3 +86,22 @@ def test_device_trim_equals_host_trim_and_oracle(tts):
         for w, rw, b, h in zip(wavs, ref_wavs, bounds, host):
             assert np.array_equal(w, rw)
             assert b == h == trim_oracle.trim_bounds(torch.from_numpy(rw), db), (db, b, h)
+
+
+def test_results_do_not_depend_on_sharding(tts):
+    """Multi-GPU invariant: utterances are keyed by (seed, utterance id), so serving ids 0..3 as one batch
+    of four, or as two shards of two (what ranks 0 and 1 of a 2-GPU job would each run, `utt_base` = first id of the
+    shard), yields the same L0 codes and the same waveforms."""
+    cfg = InferenceConfig(generate_max_len_override=48, deep_clone=True)
+    texts = ["one", "two two", "three", "4"]
+    refs = [torch.full((2400,), 0.1 * (i + 1)) for i in range(4)]
+    trs = ["a b", "c", "d e f", "g"]
+    whole = tts.tts_batch(texts, refs, trs, cfg, seed=11, utt_base=0)
+    shard0 = tts.tts_batch(texts[:2], refs[:2], trs[:2], cfg, seed=11, utt_base=0)
+    shard1 = tts.tts_batch(texts[2:], refs[2:], trs[2:], cfg, seed=11, utt_base=2)
+    for (c, w), (c2, w2) in zip(whole, shard0 + shard1):
+        assert torch.equal(c, c2)
+        assert w.shape == w2.shape and torch.equal(w, w2)
+    # and a different seed or utterance id is a different stream
+    other = tts.tts_batch(texts[:1], refs[:1], trs[:1], cfg, seed=12, utt_base=0)
+    assert not (other[0][1].shape == whole[0][1].shape and torch.equal(other[0][1], whole[0][1]))
