@@ -170,6 +170,14 @@ int m5_vocode_trim(m5_ctx* ctx, int32_t B, const int32_t* codes, const int32_t* 
                    int32_t mem, float top_db, int32_t frame_length, int32_t hop_length, float* wav_out, int64_t* start,
                    int64_t* end);
 
+/* ---- Encodec 24 kHz encoder + RVQ: replaces `self.codec.encode(ref_audio[None])` at
+ * inference.py:233 (EncodecModel.encodec_model_24khz() at 6 kbps, inference.py:87-88) for B reference clips at once.
+ * wav [sum n_samples] fp32 mono 24 kHz (HOST or DEVICE per `mem`), n_samples [B] (host); codes_out [sum ceil(n_b/320)][n_q]
+ * int32, clip after clip, n_q = 8 at 6 kbps.  Needs the "enc.*" tensors in the table passed to m5_create
+ * (mars5_tts_b200.weights.repack_encodec); M5_ERR_MISSING_WEIGHT otherwise. */
+int m5_encodec_encode(m5_ctx* ctx, int32_t B, const float* wav, const int32_t* n_samples, int32_t mem, int32_t n_q,
+                      int32_t* codes_out);
+
 /* ---- Tokenisers either side of the path (host code, no GPU work) ----------------------------
  * Merge engine for the two "minbpe v1" tokenisers: text (base = 256 bytes, mars5/minbpe/regex.py) and speech
  * (base = 1024 Encodec L0 codes, mars5/minbpe/codebook.py).  The regex split of text into chunks and the special-token

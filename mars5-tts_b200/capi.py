@@ -60,6 +60,7 @@ _SIGS = {
     "m5_ar_forward": (_I, [_P, _I, _P, _P, _P, _P, _I, _P]),
     "m5_vocode": (_I, [_P, _I, _P, _P, _I, _I, _P]),
     "m5_vocode_trim": (_I, [_P, _I, _P, _P, _I, _I, C.c_float, _I, _I, _P, _P, _P]),
+    "m5_encodec_encode": (_I, [_P, _I, _P, _P, _I, _I, _P]),
     "m5_dbg_gemm": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I]),
     "m5_dbg_skinny": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _I]),
     "m5_dbg_norm": (_I, [_P, _P, _I, _I, _P, _P, C.c_float, _I, _P, _P]),

@@ -66,6 +66,68 @@ __global__ void __launch_bounds__(256) norm_rows_kernel(NormCall p) {
   }
 }
 
+// Register-resident variant for the row widths of the hot path (D = 128 * NV: 1024 NAR, 1536 AR, 384 vocoder): the row is
+// loaded ONCE (NV float4 per lane, all loads in flight together), statistics and outputs come from registers.  Element
+// assignment and summation order equal norm_rows_kernel's (lane-strided float4, warp butterfly), so results are bit-identical.
+template <int NV>
+__global__ void __launch_bounds__(256) norm_rows_reg_kernel(NormCall p) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.M) return;
+  const int src = p.row_map ? p.row_map[row] : row;
+  const float* x = p.x + (size_t)src * p.ldx;
+  constexpr int D = 128 * NV;
+  float4 v[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) v[j] = *reinterpret_cast<const float4*>(x + lane * 4 + 128 * j);
+  float s = 0.f, ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    s += v[j].x + v[j].y + v[j].z + v[j].w;
+    ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  float mean = 0.f, rstd;
+  if (p.rms) {
+    rstd = rsqrtf(ss / D + p.eps);
+  } else {
+    mean = s / D;
+    float vs = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      vs += a * a + b * b + c * c + d * d;
+    }
+    vs = warp_sum(vs);
+    rstd = rsqrtf(vs / D + p.eps);
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane * 4 + 128 * j;
+    float y[4] = {(v[j].x - mean) * rstd, (v[j].y - mean) * rstd, (v[j].z - mean) * rstd, (v[j].w - mean) * rstd};
+    if (p.gamma) {
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma + i));
+      y[0] *= gm.x; y[1] *= gm.y; y[2] *= gm.z; y[3] *= gm.w;
+    }
+    if (p.beta) {
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(p.beta + i));
+      y[0] += bt.x; y[1] += bt.y; y[2] += bt.z; y[3] += bt.w;
+    }
+    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ldo + i) = make_float4(y[0], y[1], y[2], y[3]);
+    if (p.out) {
+      const __half h0 = __float2half_rn(y[0]), h1 = __float2half_rn(y[1]), h2 = __float2half_rn(y[2]), h3 = __float2half_rn(y[3]);
+      *reinterpret_cast<uint2*>(p.out + (size_t)row * p.ldo + i) =
+          make_uint2((uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16), (uint32_t)__half_as_ushort(h2) | ((uint32_t)__half_as_ushort(h3) << 16));
+      if (p.out_lo) {
+        const __half2 l0 = __floats2half2_rn(y[0] - __half2float(h0), y[1] - __half2float(h1));
+        const __half2 l1 = __floats2half2_rn(y[2] - __half2float(h2), y[3] - __half2float(h3));
+        *reinterpret_cast<uint2*>(p.out_lo + (size_t)row * p.ldo + i) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+      }
+    }
+  }
+}
+
 // Few rows (AR decode: M = batch): one CTA per row so that the whole row is in flight at once (latency-bound case).
 __global__ void __launch_bounds__(256) norm_row_cta_kernel(NormCall p) {
   pdl_launch_dependents();
@@ -141,7 +203,13 @@ int norm_rows(const NormCall& c, cudaStream_t stream) {
     return launch_k(norm_row_cta_kernel, dim3(c.M), dim3(256), 0, stream, c) == cudaSuccess ? M5_OK : M5_ERR_CUDA;
   }
   const int wpb = 8;
-  norm_rows_kernel<<<(c.M + wpb - 1) / wpb, wpb * 32, 0, stream>>>(c);
+  const dim3 grid((c.M + wpb - 1) / wpb), block(wpb * 32);
+  const bool aligned = ((size_t)c.x % 16 == 0) && (!c.out || (size_t)c.out % 8 == 0) && (!c.out_lo || (size_t)c.out_lo % 8 == 0) &&
+                       (!c.out_f32 || (size_t)c.out_f32 % 16 == 0);
+  if (aligned && c.D == 1024) norm_rows_reg_kernel<8><<<grid, block, 0, stream>>>(c);
+  else if (aligned && c.D == 1536) norm_rows_reg_kernel<12><<<grid, block, 0, stream>>>(c);
+  else if (aligned && c.D == 384) norm_rows_reg_kernel<3><<<grid, block, 0, stream>>>(c);
+  else norm_rows_kernel<<<grid, block, 0, stream>>>(c);
   return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
 }
 

@@ -63,7 +63,7 @@ class Engine:
     rank 0 repacks, the blob is broadcast over NCCL, see dist.py)."""
 
     def __init__(self, ar_sd=None, nar_sd=None, voc_sd=None, text_vocab_len=None, device=0, max_pos=4096,
-                 packed=None):
+                 packed=None, enc_sd=None):
         if not torch.cuda.is_available():
             raise RuntimeError("mars5_tts_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = capi.load()
@@ -72,6 +72,9 @@ class Engine:
             dims = weights.dims_from_state(ar_sd, nar_sd, voc_sd, text_vocab_len)
             tensors, alphas = weights.repack(ar_sd, nar_sd, voc_sd, dims, max_pos=max_pos)
             packed = {"dims": dims, "alphas": alphas, "tensors": tensors, "max_pos": max_pos}
+        if enc_sd is not None:   # Encodec encoder + RVQ weights: enables encodec_encode()
+            packed = dict(packed, tensors={**packed["tensors"], **weights.repack_encodec(enc_sd)})
+        self.has_encodec = any(k.startswith("enc.") for k in packed["tensors"])
         self.dims, self.alphas = packed["dims"], packed["alphas"]
         dev = torch.device("cuda", self.device)
         self.tensors = {k: (v if v.is_cuda else v.to(dev)) for k, v in packed["tensors"].items()}
@@ -226,6 +229,22 @@ class Engine:
         offs = np.concatenate([[0], np.cumsum(xlen)])
         return [out[offs[b]:offs[b + 1]] for b in range(B)]
 
+    # ------------------------------------------------------------------------------------------ Encodec encoder
+    def encodec_encode(self, wavs, n_q=8):
+        """wavs: list of mono 24 kHz waveforms (1-D float arrays / tensors).  Returns a list of (T_b, n_q) int32 code arrays,
+        T_b = ceil(len / 320) -- what EncodecModel.encode gives for each clip (inference.py:233), for the whole batch at once."""
+        if not self.has_encodec:
+            raise capi.M5Error("this Engine was built without Encodec weights (pass enc_sd=EncodecModel.state_dict())")
+        arrs = [np.ascontiguousarray(np.asarray(w.detach().cpu() if torch.is_tensor(w) else w, dtype=np.float32).reshape(-1)) for w in wavs]
+        ns = _i32([len(a) for a in arrs])
+        flat = np.ascontiguousarray(np.concatenate(arrs))
+        frames = [(int(n) + 319) // 320 for n in ns]
+        out = np.zeros((int(np.sum(frames)), n_q), dtype=np.int32)
+        rc = self.lib.m5_encodec_encode(self.ctx, len(arrs), capi.ptr(flat), capi.ptr(ns), capi.MEM_HOST, int(n_q), capi.ptr(out))
+        capi.check(self.ctx, rc, "m5_encodec_encode")
+        offs = np.concatenate([[0], np.cumsum(frames)])
+        return [out[offs[b]:offs[b + 1]] for b in range(len(arrs))]
+
     # ------------------------------------------------------------------------------------------ vocoder
     def vocode_packed(self, codes, n_frames, bandwidth_id=1):
         mem, nf_a = self._mem(codes), _i32(n_frames)
@@ -265,7 +284,7 @@ class Mars5TTS:
     """
 
     def __init__(self, ar_ckpt, nar_ckpt, device: Optional[str] = None, *, vocos_state=None, texttok=None,
-                 speechtok=None, codec=None):
+                 speechtok=None, codec=None, encodec_state=None):
         if texttok is None or speechtok is None:
             # "minbpe v1" model texts stored in the checkpoint (inference.py:92-99), on the native merge engine (bpe.py)
             from . import bpe
@@ -278,12 +297,14 @@ class Mars5TTS:
         if codec is None:
             # like the reference (inference.py:87-88): EncodecModel.encodec_model_24khz() at 6 kbps on the device.  The Encodec
             # ENCODER is outside the hot path (third-party package); it is only needed by tts().
-            try:
-                from encodec import EncodecModel
-                codec = EncodecModel.encodec_model_24khz().to(self.device).eval()
-                codec.set_target_bandwidth(6.0)
-            except ImportError:
-                codec = None   # tts() raises with instructions; vocode() / the Engine keep working
+            # When the package imports, only its WEIGHTS are taken: the encoder + RVQ run in libmars5_b200.so (csrc/encodec.cu,
+            # batched over the reference clips); `encodec_state=` passes such a state dict directly.
+            if encodec_state is None:
+                try:
+                    from encodec import EncodecModel
+                    encodec_state = EncodecModel.encodec_model_24khz().state_dict()
+                except ImportError:
+                    encodec_state = None   # tts() raises with instructions; vocode() / the Engine keep working
         if vocos_state is None:
             # like the reference (inference.py:119-121): Vocos.from_pretrained("charactr/vocos-encodec-24khz"), weight norm
             # folded; only its state dict is used -- the network itself runs in libmars5_b200.so
@@ -295,7 +316,8 @@ class Mars5TTS:
                                    "Vocos.from_pretrained('charactr/vocos-encodec-24khz')> to Mars5TTS (the vocoder network runs "
                                    "inside libmars5_b200.so, only its weights are needed)") from None
         self.texttok, self.speechtok, self.codec = texttok, speechtok, codec
-        self.engine = Engine(ar_ckpt["model"], nar_ckpt["model"], vocos_state, len(texttok.vocab), device=self.device.index)
+        self.engine = Engine(ar_ckpt["model"], nar_ckpt["model"], vocos_state, len(texttok.vocab), device=self.device.index,
+                             enc_sd=encodec_state if codec is None else None)
         self.n_vocab = len(texttok.vocab) + len(speechtok.vocab)
         self.n_text_vocab = len(texttok.vocab) + 1
         self.diffusion_n_classes = 1025
@@ -323,15 +345,24 @@ class Mars5TTS:
         if ref_audio.shape[0] != 1:
             ref_audio = ref_audio.mean(dim=0, keepdim=True)
         ref_audio = torch.nn.functional.pad(ref_audio, (int(self.sr * cfg.ref_audio_pad), 0))
+        if self.codec is None and self.engine.has_encodec:
+            codes = self.engine.encodec_encode([ref_audio[0]])[0]          # (T, 8) on the device-side encoder
+            prompt_codec = torch.from_numpy(codes.astype(np.int64)).T[None]  # (1, n_q, T) like EncodecModel.encode
+            return self._prepare_with_codes(text, ref_transcript, cfg, prompt_codec)
         if self.codec is None:
-            raise RuntimeError("no Encodec codec: `encodec` is not importable and no codec= was passed to Mars5TTS "
-                               "(anything with encode(wav[None]) -> [(codes (1, 8, T), scale)] works)")
+            raise RuntimeError("no Encodec codec: `encodec` is not importable and neither codec= nor encodec_state= was passed to "
+                               "Mars5TTS (codec: anything with encode(wav[None]) -> [(codes (1, 8, T), scale)])")
         wav_in = ref_audio[None]
         if hasattr(self.codec, "parameters"):   # an nn.Module codec lives on its own device (the reference moves the clip there)
             p0 = next(iter(self.codec.parameters()), None)
             if p0 is not None:
                 wav_in = wav_in.to(p0.device)
         prompt_codec = self.codec.encode(wav_in)[0][0]  # (1, n_q, T)
+        return self._prepare_with_codes(text, ref_transcript, cfg, prompt_codec)
+
+    def _prepare_with_codes(self, text, ref_transcript, cfg, prompt_codec):
+        tt = self.texttok
+        text_tokens = tt.encode("<|startoftext|>" + text.strip() + "<|endoftext|>", allowed_special="all")
         l0 = prompt_codec[0, 0].tolist()
         speech_tokens = self.speechtok.encode(" ".join(str(t) for t in l0).strip())
         spk_ref = prompt_codec[0].T.cpu().numpy().astype(np.int32)  # (T, n_q)

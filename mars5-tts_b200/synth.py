@@ -139,6 +139,36 @@ def make_vocos_state(size, seed=2, n_fft=1280, n_bw=4, n_codebooks=16):
     return sd
 
 
+def make_encodec_state(seed=3, n_filters=32, dimension=128, n_codebooks=32, bins=1024):
+    """Encodec 24 kHz encoder + RVQ state dict with encodec's own module names after weight norm has been folded
+    (oracle/encodec_oracle.py header): seeded random fp32 values at the real shapes (n_filters / dimension can be shrunk for
+    tests; the released model is n_filters=32, dimension=128, 32 codebooks of 1024 x 128)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def conv(co, ci, k):
+        return torch.randn(co, ci, k, generator=g) * (1.0 / (ci * k) ** 0.5), torch.randn(co, generator=g) * 0.02
+
+    sd, p = {}, "encoder.model."
+    sd[p + "0.conv.conv.weight"], sd[p + "0.conv.conv.bias"] = conv(n_filters, 1, 7)
+    idx, mult = 1, 1
+    for ratio in (2, 4, 5, 8):
+        dim = mult * n_filters
+        sd[p + f"{idx}.block.1.conv.conv.weight"], sd[p + f"{idx}.block.1.conv.conv.bias"] = conv(dim // 2, dim, 3)
+        sd[p + f"{idx}.block.3.conv.conv.weight"], sd[p + f"{idx}.block.3.conv.conv.bias"] = conv(dim, dim // 2, 1)
+        sd[p + f"{idx}.shortcut.conv.conv.weight"], sd[p + f"{idx}.shortcut.conv.conv.bias"] = conv(dim, dim, 1)
+        sd[p + f"{idx + 2}.conv.conv.weight"], sd[p + f"{idx + 2}.conv.conv.bias"] = conv(2 * dim, dim, 2 * ratio)
+        idx += 3
+        mult *= 2
+    H = mult * n_filters
+    for layer in range(2):
+        for nm, shape in (("weight_ih", (4 * H, H)), ("weight_hh", (4 * H, H)), ("bias_ih", (4 * H,)), ("bias_hh", (4 * H,))):
+            sd[p + f"{idx}.lstm.{nm}_l{layer}"] = torch.randn(*shape, generator=g) * (1.0 / H ** 0.5)
+    sd[p + f"{idx + 2}.conv.conv.weight"], sd[p + f"{idx + 2}.conv.conv.bias"] = conv(dimension, H, 7)
+    for q in range(n_codebooks):
+        sd[f"quantizer.vq.layers.{q}._codebook.embed"] = torch.randn(bins, dimension, generator=g) * (0.7 ** q)
+    return sd
+
+
 class ByteTextTok:
     """Minimal stand-in with the reference tokenizers' interface (minbpe v1, no merges): 256 bytes + 2 specials."""
 

@@ -193,6 +193,32 @@ def repack(ar_sd, nar_sd, voc_sd, dims, max_pos=4096, n_t=1000):
     return {k: v.contiguous() for k, v in t.items()}, alphas
 
 
+def repack_encodec(enc_sd, n_q=8):
+    """Encodec 24 kHz encoder + RVQ state dict (EncodecModel.state_dict(), with or without weight norm folded) -> the "enc.*"
+    fp32 tensors csrc/encodec.cu consumes.  Key names: oracle/encodec_oracle.py header."""
+    def w_of(prefix):
+        if prefix + ".weight" in enc_sd:
+            return enc_sd[prefix + ".weight"].float()
+        g, v = enc_sd[prefix + ".weight_g"].float(), enc_sd[prefix + ".weight_v"].float()   # torch weight_norm, dim=0
+        return v * (g / v.flatten(1).norm(dim=1).reshape(-1, *([1] * (v.dim() - 1))))
+
+    t, p = {}, "encoder.model."
+    t["enc.c0.w"], t["enc.c0.b"] = w_of(p + "0.conv.conv"), enc_sd[p + "0.conv.conv.bias"].float()
+    idx = 1
+    for s in range(4):
+        for nm, key in (("a", f"{idx}.block.1.conv.conv"), ("b", f"{idx}.block.3.conv.conv"), ("s", f"{idx}.shortcut.conv.conv")):
+            t[f"enc.r{s}.{nm}.w"], t[f"enc.r{s}.{nm}.b"] = w_of(p + key), enc_sd[p + key + ".bias"].float()
+        t[f"enc.d{s}.w"], t[f"enc.d{s}.b"] = w_of(p + f"{idx + 2}.conv.conv"), enc_sd[p + f"{idx + 2}.conv.conv.bias"].float()
+        idx += 3
+    for l in range(2):
+        t[f"enc.lstm{l}.ih.w"], t[f"enc.lstm{l}.ih.b"] = enc_sd[p + f"{idx}.lstm.weight_ih_l{l}"].float(), enc_sd[p + f"{idx}.lstm.bias_ih_l{l}"].float()
+        t[f"enc.lstm{l}.hh.w"], t[f"enc.lstm{l}.hh.b"] = enc_sd[p + f"{idx}.lstm.weight_hh_l{l}"].float(), enc_sd[p + f"{idx}.lstm.bias_hh_l{l}"].float()
+    t["enc.final.w"], t["enc.final.b"] = w_of(p + f"{idx + 2}.conv.conv"), enc_sd[p + f"{idx + 2}.conv.conv.bias"].float()
+    for q in range(n_q):
+        t[f"enc.cb{q}"] = enc_sd[f"quantizer.vq.layers.{q}._codebook.embed"].float()
+    return {k: v.contiguous() for k, v in t.items()}
+
+
 def make_cfg(dims, alphas, max_pos):
     cfg = capi.ModelCfg()
     for k, v in dims.items():
