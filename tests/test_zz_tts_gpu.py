@@ -101,7 +101,9 @@ def test_results_do_not_depend_on_sharding(tts):
     shard1 = tts.tts_batch(texts[2:], refs[2:], trs[2:], cfg, seed=11, utt_base=2)
     for (c, w), (c2, w2) in zip(whole, shard0 + shard1):
         assert torch.equal(c, c2)
-        assert w.shape == w2.shape and torch.equal(w, w2)
+        # same discrete codes => same audio up to the vocoder GEMMs' tile choice (it depends on the batch's total frame count
+        # and changes the fp32 accumulation order): a flipped NAR code would show as an O(0.1) difference
+        assert w.shape == w2.shape and float((w - w2).abs().max()) < 1e-4 * max(1.0, float(w.abs().max()))
     # and a different seed or utterance id is a different stream
     other = tts.tts_batch(texts[:1], refs[:1], trs[:1], cfg, seed=12, utt_base=0)
     assert not (other[0][1].shape == whole[0][1].shape and torch.equal(other[0][1], whole[0][1]))
