@@ -115,3 +115,63 @@ def test_repack_consumes_the_released_checkpoint_layout():
     # the synthetic FULL-size checkpoints of bench.py have exactly this layout
     full = synth.FULL
     assert full["n_text"] + full["n_speech"] == d["ar_vocab"] and full["ar_layers"] == d["ar_layers"] and full["nar_dec_layers"] == d["nar_dec_layers"]
+
+
+def test_vocos_codebook_stride_is_the_encodec_bin_count():
+    """ADVICE r1 (high): the released vocos table concatenates the codebooks of the MAXIMUM bandwidth (16 x 1024 rows);
+    codes_to_features offsets codebook q by q * 1024 whatever the table holds.  dims / oracle must not derive the stride
+    from the row count."""
+    from oracle import vocos_oracle
+    size = synth.TINY
+    ar, nar = synth.make_ar_state(size), synth.make_nar_state(size)
+    v16, v8 = synth.make_vocos_state(size, n_codebooks=16), synth.make_vocos_state(size, n_codebooks=8)
+    assert v16["feature_extractor.codebook_weights"].shape[0] == 16 * 1024
+    assert weights.dims_from_state(ar, nar, v16, size["n_text"])["voc_codebook"] == 1024
+    assert weights.dims_from_state(ar, nar, v8, size["n_text"])["voc_codebook"] == 1024
+    # same first 8 x 1024 rows -> same audio, independent of how many codebooks follow
+    v8["feature_extractor.codebook_weights"] = v16["feature_extractor.codebook_weights"][: 8 * 1024].clone()
+    for k in v16:
+        if k != "feature_extractor.codebook_weights":
+            v8[k] = v16[k]
+    codes = torch.randint(0, 1024, (5, 8), generator=torch.Generator().manual_seed(0))
+    assert torch.equal(vocos_oracle.vocos_forward(v16, codes, 1), vocos_oracle.vocos_forward(v8, codes, 1))
+    import pytest
+    bad = dict(v16)
+    bad["feature_extractor.codebook_weights"] = v16["feature_extractor.codebook_weights"][:4096]
+    with pytest.raises(ValueError):
+        weights.dims_from_state(ar, nar, bad, size["n_text"])
+
+
+def test_repack_encodec_folds_weight_norm_and_oracle_shapes():
+    """weights.repack_encodec accepts EncodecModel.state_dict() with weight norm still attached (weight_g / weight_v) or
+    folded; the oracle yields ceil(samples / 320) frames of 8 codes."""
+    from oracle import encodec_oracle
+    sd = synth.make_encodec_state(n_filters=4, dimension=16, n_codebooks=8, bins=32)
+    t = weights.repack_encodec(sd)
+    wn = {}
+    for k, v in sd.items():
+        if k.endswith(".conv.conv.weight"):
+            norm = v.flatten(1).norm(dim=1).reshape(-1, 1, 1)
+            wn[k[:-len("weight")] + "weight_g"], wn[k[:-len("weight")] + "weight_v"] = norm * 1.0, v * 3.0   # g = |w|, v = any multiple
+        else:
+            wn[k] = v
+    t2 = weights.repack_encodec(wn)
+    assert set(t) == set(t2)
+    for k in t:
+        assert torch.allclose(t[k], t2[k], atol=1e-6), k
+    assert t["enc.c0.w"].shape == (4, 1, 7) and t["enc.d3.w"].shape == (64, 32, 16) and t["enc.lstm1.hh.w"].shape == (256, 64)
+    for n in (1, 320, 321, 999):
+        assert encodec_oracle.encode(sd, torch.randn(n)).shape == ((n + 319) // 320, 8)
+
+
+def test_nar_cfg_and_ar_cfg_carry_every_inference_field():
+    from mars5_tts_b200 import capi
+    from mars5_tts_b200.engine import Engine, InferenceConfig
+    e = object.__new__(Engine)
+    e._sched_cache = {}
+    ic = InferenceConfig(typical_p=0.6, top_k=50, x_0_temp=0.5, nar_guidance_w=2.0, q0_override_steps=7, deep_clone=False)
+    a = Engine.make_ar_cfg(e, ic, 321, 99)
+    assert abs(a.typical_p - 0.6) < 1e-7 and a.top_k == 50 and a.max_len == 321 and a.eos_id == 99
+    n = Engine.make_nar_cfg(e, ic, T=10, jump_len=2, jump_n_sample=3)
+    assert (n.T, n.q0_override_steps, n.deep_clone, n.precise, n.jump_len, n.jump_n_sample, n.scaled_forward) == (10, 7, 0, capi.NUM_MIXED, 2, 3, 0)
+    assert abs(n.x0_temp - 0.5) < 1e-7 and abs(n.guidance_w - 2.0) < 1e-7
