@@ -396,7 +396,9 @@ def main():
     ap.add_argument("--ntok", type=int, default=0, help="profiling aid: override the target-text token count (N = 15 * ntok)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--also-fast", action="store_true", help="also time one step in fast mode and report it beside the headline")
+    ap.add_argument("--also-fast", dest="also_fast", action="store_true", default=True,
+                    help="also time one step in fast mode and report it beside the headline (default: on, when the wall budget allows)")
+    ap.add_argument("--no-also-fast", dest="also_fast", action="store_false")
     args = ap.parse_args()
     if args.precise >= 0:
         args.mode = "precise" if args.precise else "fast"
@@ -555,7 +557,7 @@ def main():
     e2e_steps = 1  # one end-to-end step keeps the default run within minutes
     ms_e2e, wavs = (ms / n_steps, None) if (args.no_e2e or nar_only) else timed(e2e_steps, step_host)
     fast_ms = None
-    if args.also_fast and mode != 0:
+    if args.also_fast and mode != 0 and t_full_ms is not None and allmax(elapsed()) + 0.8 * t_full_ms / 1e3 + 60 < BUDGET_S:
         fast_ms, _ = timed(1, lambda: step_dev(mode_=0))
     audio_total = wl["audio_s"] * world * n_steps
     value = audio_total / (ms / 1e3)
