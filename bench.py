@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 METRIC = "audio sec/s synthesized (deep-clone, batch 32)"
 UNIT = "audio_s/s"
 BUDGET_S = float(os.environ.get("M5_BENCH_BUDGET_S", "780"))
-MODES = {"fast": 0, "precise": 1, "mixed": 2}
+MODES = {"fast": 0, "precise": 1, "mixed": 2, "mixed8": 3}
 
 
 def elapsed():

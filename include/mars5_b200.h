@@ -31,6 +31,7 @@ extern "C" {
 
 #define M5_DT_F16 0
 #define M5_DT_F32 1
+#define M5_DT_U8 2 /* fp8 (e4m3) weight copies of the mixed8 numerics, one byte per element */
 
 typedef struct m5_ctx m5_ctx;
 
@@ -120,7 +121,9 @@ typedef struct {
                        *               1 precise = every activation operand is an fp16 (hi, lo) pair (1e-5 on the logits);
                        *               2 mixed   = GEMM activations, keys and values are pairs, queries and probabilities
                        *                           single fp16, attention on tcgen05: the cheapest setting that keeps the
-                       *                           logits within 1e-3 max-abs of the fp32 reference */
+                       *                           logits within 1e-3 max-abs of the fp32 reference
+                       *               3 mixed8  = mixed, with the lo half of the big decoder GEMMs' activation pairs as an
+                       *                           fp8 (e5m2 x e4m3) tcgen05 pass into the same accumulator */
   /* optional HOST tables [4][T]: log_alpha, log_1_min_alpha, log_cumprod_alpha, log_1_min_cumprod_alpha
    * (MultinomialDiffusion.__init__, diffuser.py:76-95); NULL -> computed inside the library */
   const float* schedule;
@@ -217,6 +220,10 @@ int m5_trim_bounds(int32_t B, const float* wav, const int64_t* offsets, float to
 int m5_dbg_gemm(m5_ctx* ctx, const void* A_f16, const void* W_f16, int32_t M, int32_t N, int32_t K, int32_t kwrap,
                 const float* bias, const float* colscale, void* out, void* out_lo, int32_t ldc, int32_t mode,
                 int32_t act, int32_t accumulate, int32_t force_bn);
+/* fp16 hi pass + fp8 lo pass into one accumulator (mixed8): out[M][N] fp32 = A16[M][K] W16[N][K]^T + A8[M][K] W8[N][K]^T, A8 e5m2
+ * (lo halves x 2^-2), W8 e4m3 (weights x 2^+2); CTA-pair kernel (M, N large enough), K % 128 == 0. */
+int m5_dbg_gemm_f8lo(m5_ctx* ctx, const void* A16, int32_t lda, const void* A8, const void* W16, const void* W8, int32_t M,
+                     int32_t N, int32_t K, float* out, int32_t ldc);
 int m5_dbg_skinny(m5_ctx* ctx, const void* X_f16, const void* W_f16, int32_t B, int32_t N, int32_t K, float* out_f32,
                   void* out_f16, int32_t ldc, int32_t swiglu, int32_t accumulate);
 int m5_dbg_norm(m5_ctx* ctx, const float* x, int32_t M, int32_t D, const float* gamma, const float* beta, float eps,

@@ -8,10 +8,10 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmars5_b200.so")
 
 M5_OK = 0
 MEM_HOST, MEM_DEVICE = 0, 1
-DT_F16, DT_F32 = 0, 1
+DT_F16, DT_F32, DT_U8 = 0, 1, 2
 OUT_F32, OUT_F16, OUT_SWIGLU_F16, OUT_F16_SPLIT, OUT_SWIGLU_F16_SPLIT = 0, 1, 2, 3, 4
 ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
-NUM_FAST, NUM_PRECISE, NUM_MIXED = 0, 1, 2   # m5_nar_cfg.precise (NAR numerics)
+NUM_FAST, NUM_PRECISE, NUM_MIXED, NUM_MIXED8 = 0, 1, 2, 3   # m5_nar_cfg.precise (NAR numerics)
 
 
 class ModelCfg(C.Structure):
@@ -62,6 +62,7 @@ _SIGS = {
     "m5_vocode_trim": (_I, [_P, _I, _P, _P, _I, _I, C.c_float, _I, _I, _P, _P, _P]),
     "m5_encodec_encode": (_I, [_P, _I, _P, _P, _I, _I, _P]),
     "m5_dbg_gemm": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I]),
+    "m5_dbg_gemm_f8lo": (_I, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _P, _I]),
     "m5_dbg_skinny": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _I]),
     "m5_dbg_norm": (_I, [_P, _P, _I, _I, _P, _P, C.c_float, _I, _P, _P]),
     "m5_dbg_attn": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I]),

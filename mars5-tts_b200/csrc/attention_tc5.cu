@@ -24,6 +24,7 @@
 // tile) ran at 413 TFLOP/s on the NAR shape; one-pass lazy softmax with O in TMEM 551; S issued ahead of PV 620; this
 // 64-key ring 610 with the tensor round trip gone -- what is left is per-tile instruction overhead and MUFU.EX2.
 #include <cuda.h>
+#include <cuda_fp8.h>
 
 #include "m5_internal.h"
 #include "ptx.cuh"
@@ -84,6 +85,7 @@ M5_DEVINL float fmax3(float a, float b, float c) {
 struct AttnTc5Params {
   const int* q_start; const int* q_len; const int* k_start; const int* k_len;
   __half* O; __half* Olo; int ldo;
+  uint8_t* Olo8; int ldo8;   // SPLIT: lo half of the output as e5m2 scaled by 2^-2 instead of fp16 (mixed8 numerics)
   float scale_log2;
 };
 
@@ -350,6 +352,7 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint32_t h[4], l[4];
+          uint32_t l8[2] = {0u, 0u};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float v0 = __uint_as_float(r[i + 2 * e]) * inv, v1 = __uint_as_float(r[i + 2 * e + 1]) * inv;
@@ -357,10 +360,18 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (SPLIT) {
               const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[e]));
               l[e] = pack_half2(v0 - f.x, v1 - f.y);
+              if (p.Olo8) {
+                const uint32_t b0 = (uint32_t)__nv_cvt_float_to_fp8((v0 - f.x) * 0.25f, __NV_SATFINITE, __NV_E5M2);
+                const uint32_t b1 = (uint32_t)__nv_cvt_float_to_fp8((v1 - f.y) * 0.25f, __NV_SATFINITE, __NV_E5M2);
+                l8[e >> 1] |= (b0 | (b1 << 8)) << (16 * (e & 1));
+              }
             }
           }
           *reinterpret_cast<uint4*>(og + base + i) = make_uint4(h[0], h[1], h[2], h[3]);
-          if (SPLIT) *reinterpret_cast<uint4*>(p.Olo + ooff + base + i) = make_uint4(l[0], l[1], l[2], l[3]);
+          if (SPLIT) {
+            if (p.Olo8) *reinterpret_cast<uint2*>(p.Olo8 + (size_t)(p.q_start[seq] + q0 + row) * p.ldo8 + head * AT_HD + base + i) = make_uint2(l8[0], l8[1]);
+            else *reinterpret_cast<uint4*>(p.Olo + ooff + base + i) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
         }
       };
       store32(ra, 0);
@@ -407,7 +418,7 @@ int flash_attn_tc5(const AttnCall& c, cudaStream_t stream) {
   if (c.causal || c.q_rows <= 0 || c.k_rows <= 0) return M5_ERR_ARG;
   if ((c.ldq | c.ldk | c.ldv | c.ldo) % 8 != 0) return M5_ERR_ARG;
   const bool split = c.Klo != nullptr;   // keys / values as (hi, lo) pairs, O written as a pair; Q and P stay single fp16
-  if (split && (!c.Vlo || !c.Olo)) return M5_ERR_ARG;
+  if (split && (!c.Vlo || !(c.Olo || c.Olo8))) return M5_ERR_ARG;
   CUtensorMap tq, tk, tv, tkl, tvl;
   const uint64_t cols = (uint64_t)c.n_heads * AT_HD;
   if (at_tmap(&tq, c.Q, c.q_rows, cols, c.ldq, AT_BQ) != M5_OK) return M5_ERR_CUDA;
@@ -425,6 +436,7 @@ int flash_attn_tc5(const AttnCall& c, cudaStream_t stream) {
   }
   AttnTc5Params p;
   p.q_start = c.q_start; p.q_len = c.q_len; p.k_start = c.k_start; p.k_len = c.k_len; p.O = c.O; p.Olo = c.Olo; p.ldo = c.ldo;
+  p.Olo8 = c.Olo8; p.ldo8 = c.ldo8;
   p.scale_log2 = c.scale * 1.4426950408889634f;
   dim3 grid((c.max_q + AT_BQ - 1) / AT_BQ, c.n_heads, c.n_seqs);
   if (split) flash_tc5_kernel<true><<<grid, AT_THREADS, AtCfg<true>::SMEM, stream>>>(tq, tk, tv, tkl, tvl, p);

@@ -182,6 +182,19 @@ int m5_dbg_gemm(m5_ctx* ctx, const void* A, const void* Wt, int32_t M, int32_t N
   return M5_OK;
 }
 
+int m5_dbg_gemm_f8lo(m5_ctx* ctx, const void* A16, int32_t lda, const void* A8, const void* W16, const void* W8, int32_t M,
+                     int32_t N, int32_t K, float* out, int32_t ldc) {
+  if (!ctx || !A16 || !A8 || !W16 || !W8 || !out) return M5_ERR_ARG;
+  GemmCall g;
+  g.A = (const __half*)A16; g.W = (const __half*)W16; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = K;
+  g.A8 = (const uint8_t*)A8; g.W8 = (const uint8_t*)W8; g.K8 = K; g.lda8 = K; g.ldw8 = K;
+  g.out = out; g.ldc = ldc; g.mode = M5_OUT_F32;
+  int r = gemm_tc5(g, ctx->stream, ctx->num_sms);
+  if (r != M5_OK) return ctx->fail(r, "gemm_tc5 (fp8 lo pass) failed: shape not eligible for the CTA-pair kernel?");
+  ctx->launches += 1;
+  return M5_OK;
+}
+
 int m5_dbg_norm(m5_ctx* ctx, const float* x, int32_t M, int32_t D, const float* gamma, const float* beta, float eps,
                 int32_t rms, void* out_f16, void* out_lo_f16) {
   if (!ctx) return M5_ERR_ARG;

@@ -2,6 +2,7 @@
 // store routine and the TMA tensor-map encoder.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp8.h>
 
 #include "m5_internal.h"
 #include "ptx.cuh"
@@ -9,7 +10,10 @@
 namespace m5 {
 
 // epilogue kinds (compile-time)
-enum { E_F32 = 0, E_F32_ACC = 1, E_F16 = 2, E_SWIGLU = 3, E_GENERIC = 4, E_F16_SPLIT = 5, E_SWIGLU_SPLIT = 6 };
+enum { E_F32 = 0, E_F32_ACC = 1, E_F16 = 2, E_SWIGLU = 3, E_GENERIC = 4, E_F16_SPLIT = 5, E_SWIGLU_SPLIT = 6, E_SWIGLU_SPLIT8 = 7 };
+
+// lo half of an (hi, lo) activation pair as e5m2, scaled by 2^-2 (the fp8 weights carry 2^+2): one byte
+__device__ __forceinline__ uint8_t lo_to_e5m2(float lo) { return (uint8_t)__nv_cvt_float_to_fp8(lo * 0.25f, __NV_SATFINITE, __NV_E5M2); }
 
 struct GemmEpi {
   const float* bias;      // [N] fp32 or null
@@ -17,6 +21,8 @@ struct GemmEpi {
   void* out;              // fp32 or fp16, row stride ldc (elements)
   void* out_lo;           // split modes: low halves
   int ldc;
+  uint8_t* out_lo8;  // E_SWIGLU_SPLIT8: lo halves as e5m2
+  int ldc8;
   int mode;        // M5_OUT_*
   int act;         // M5_ACT_*
   int accumulate;  // fp32 out: out += value (residual stream update)
@@ -87,6 +93,16 @@ __device__ __forceinline__ void epi_store4(const GemmEpi& epi, float (&v)[4], co
       *reinterpret_cast<uint32_t*>(o) = pack_h2(h0, h1);
       *reinterpret_cast<uint32_t*>(ol) = pack_h2(l0, l1);
     } else if (col + 1 < N) { o[0] = h0; ol[0] = l0; }
+  } else if constexpr (KIND == E_SWIGLU_SPLIT8) {
+    __half* o = reinterpret_cast<__half*>(epi.out) + (size_t)row * epi.ldc + (col >> 1);
+    uint8_t* o8 = epi.out_lo8 + (size_t)row * epi.ldc8 + (col >> 1);
+    const float g0 = silu_f(v[0]) * v[1], g1 = silu_f(v[2]) * v[3];
+    const __half h0 = __float2half_rn(g0), h1 = __float2half_rn(g1);
+    const uint8_t l0 = lo_to_e5m2(g0 - __half2float(h0)), l1 = lo_to_e5m2(g1 - __half2float(h1));
+    if (full4) {
+      *reinterpret_cast<uint32_t*>(o) = pack_h2(h0, h1);
+      *reinterpret_cast<uint16_t*>(o8) = (uint16_t)l0 | ((uint16_t)l1 << 8);
+    } else if (col + 1 < N) { o[0] = h0; o8[0] = l0; }
   } else {  // E_GENERIC: activations, column scale, split (hi | lo) outputs -- cold paths (vocoder, timestep MLPs, precise mode)
     if (epi.act == M5_ACT_GELU) {
 #pragma unroll
@@ -160,8 +176,23 @@ static inline int make_tmap_k64(CUtensorMap* map, const void* ptr, uint64_t rows
 }
 
 
+// 2-D byte matrix [rows, cols] (fp8 operands) with row stride ld BYTES; box = [box_rows, 128 bytes], 128B swizzle.
+static inline int make_tmap_u8_k128(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return M5_ERR_CUDA;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld};
+  cuuint32_t box[2] = {128, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? M5_OK : M5_ERR_CUDA;
+}
+
 static inline int gemm_epi_kind(const GemmCall& g) {
   const bool plain = g.act == M5_ACT_NONE;
+  if (plain && g.mode == M5_OUT_SWIGLU_F16_SPLIT && !g.colscale && g.out_lo8) return E_SWIGLU_SPLIT8;
   if (plain && g.mode == M5_OUT_F32 && !g.accumulate && !g.colscale) return E_F32;
   if (plain && g.mode == M5_OUT_F32 && g.accumulate) return E_F32_ACC;
   if (plain && g.mode == M5_OUT_F16 && !g.colscale) return E_F16;

@@ -266,6 +266,7 @@ static int launch_kind(const GemmCall& g, cudaStream_t stream, int num_sms) {
   const int grid = min(num_sms, m_tiles * n_tiles);
   GemmEpi e;
   e.bias = g.bias; e.colscale = g.colscale; e.out = g.out; e.out_lo = g.out_lo; e.ldc = g.ldc;
+  e.out_lo8 = g.out_lo8; e.ldc8 = g.ldc8;
   e.mode = g.mode; e.act = g.act; e.accumulate = g.accumulate;
   gemm_tc5_kernel<BLOCK_N, KIND><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ta, tb, g.M, g.N, g.K, g.kwrap, g.awrap, e);
   return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
@@ -280,9 +281,17 @@ static int launch_bn(const GemmCall& g, cudaStream_t stream, int num_sms) {
     case E_SWIGLU: return launch_kind<BLOCK_N, E_SWIGLU>(g, stream, num_sms);
     case E_F16_SPLIT: return launch_kind<BLOCK_N, E_F16_SPLIT>(g, stream, num_sms);
     case E_SWIGLU_SPLIT: return launch_kind<BLOCK_N, E_SWIGLU_SPLIT>(g, stream, num_sms);
+    case E_SWIGLU_SPLIT8: return launch_kind<BLOCK_N, E_SWIGLU_SPLIT8>(g, stream, num_sms);
     default: return launch_kind<BLOCK_N, E_GENERIC>(g, stream, num_sms);
   }
 }
+
+static bool pair_shape_ok(int M, int N, int num_sms) {
+  auto waste = [&](int bn) { return (double)(((N + bn - 1) / bn) * bn) / N; };
+  static const bool no_pairs = getenv("M5_DISABLE_2CTA") != nullptr;
+  return !no_pairs && N >= 256 && waste(256) <= 1.12 && (long)((M + 255) / 256) * ((N + 255) / 256) >= num_sms / 2;
+}
+bool gemm_f8lo_eligible(int M, int N, int num_sms) { return pair_shape_ok(M, N, num_sms); }
 
 int gemm_tc5(const GemmCall& g, cudaStream_t stream, int num_sms) {
   if (g.M <= 0 || g.N <= 0) return M5_OK;
@@ -294,8 +303,8 @@ int gemm_tc5(const GemmCall& g, cudaStream_t stream, int num_sms) {
   const int m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
   auto waste = [&](int bn) { return (double)(((g.N + bn - 1) / bn) * bn) / g.N; };
   // Large problems run on CTA pairs (cta_group::2, 256 x 256 tiles): halves the operand bytes each SM has to ingest.
-  static const bool no_pairs = getenv("M5_DISABLE_2CTA") != nullptr;
-  const bool pair_ok = !no_pairs && g.N >= 256 && waste(256) <= 1.12 && (long)((g.M + 255) / 256) * ((g.N + 255) / 256) >= num_sms / 2;
+  const bool pair_ok = pair_shape_ok(g.M, g.N, num_sms);
+  if (g.A8 && !(pair_ok || g.force_bn == 512)) return M5_ERR_ARG;   // the fp8 lo pass exists in the CTA-pair kernel only
   if (g.force_bn == 512 || (g.force_bn == 0 && pair_ok)) return gemm_tc5_2cta(g, stream, num_sms);
   // Pick the N tile: 256 when it does not waste much, else 128 / 64.
   int bn = 256;

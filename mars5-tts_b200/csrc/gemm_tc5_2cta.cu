@@ -51,6 +51,15 @@ M5_DEVINL void tma_load_2d_2sm(void* smem_dst, const void* tmap, uint64_t* bar, 
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
       : "memory");
 }
+// fp8 operands (A e5m2, B e4m3 per the instruction descriptor): 32 K-elements = 32 bytes per instruction
+M5_DEVINL void tc5_mma_f8_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 M5_DEVINL void tc5_mma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -77,8 +86,9 @@ M5_DEVINL void mbar_arrive_leader(uint64_t* bar) {
 
 template <int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C2_THREADS, 1)
-gemm_tc5_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N,
-                     int K, int kwrap, int awrap, GemmEpi epi) {
+gemm_tc5_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const __grid_constant__ CUtensorMap tmap_a8, const __grid_constant__ CUtensorMap tmap_b8, int M, int N,
+                     int K, int kwrap, int awrap, int K8, GemmEpi epi) {
   extern __shared__ uint8_t smem_raw2[];
   uint8_t* smem = smem_raw2 + ((1024u - (smem_u32(smem_raw2) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C2_BAR_OFF);
@@ -94,6 +104,7 @@ gemm_tc5_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   const int n_tiles = (N + C2_BN - 1) / C2_BN;
   const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = K / C2_BK;
+  const int k_blocks8 = K8 / 128;   // fp8 "lo" blocks: 128 K-elements per 128-byte row, same 16 KB tiles
   const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
   constexpr uint32_t TMEM_COLS = 512;
   constexpr int M_BAND2 = 74;  // pairs: 74 x 256 rows of A stay L2-resident while N is swept
@@ -101,6 +112,7 @@ gemm_tc5_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (k_blocks8 > 0) { tma_prefetch_desc(&tmap_a8); tma_prefetch_desc(&tmap_b8); }
     for (int s = 0; s < C2_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -145,6 +157,15 @@ gemm_tc5_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kwrap > 0 ? (k0 % kwrap) : k0, n_blk * C2_BN + rank * (C2_BN / 2));
           if (++stage == C2_STAGES) { stage = 0; phase ^= 1; }
         }
+        for (int kb = 0; kb < k_blocks8; ++kb) {   // lo halves: e5m2 activations x e4m3 weights, byte-addressed maps
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C2_STAGE_BYTES;
+          uint8_t* sb = sa + C2_A_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C2_STAGE_BYTES);
+          tma_load_2d_2sm(sa, &tmap_a8, &full_bar[stage], kb * 128, m_blk * 2 * C2_BM + rank * C2_BM);
+          tma_load_2d_2sm(sb, &tmap_b8, &full_bar[stage], kb * 128, n_blk * C2_BN + rank * (C2_BN / 2));
+          if (++stage == C2_STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -168,6 +189,18 @@ gemm_tc5_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           const uint64_t db = umma_desc_k_sw128(sa + C2_A_BYTES);
 #pragma unroll
           for (int k = 0; k < C2_BK / 16; ++k) tc5_mma_f16_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          tc5_commit_mc(&empty_bar[stage]);
+          if (++stage == C2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        constexpr uint32_t idesc8 = umma_idesc_e5m2_e4m3(2 * C2_BM, C2_BN);
+        for (int kb = 0; kb < k_blocks8; ++kb) {   // same accumulator: the fp8 products are at true scale (2^-2 x 2^+2)
+          mbar_wait(&full_bar[stage], phase);
+          tc5_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C2_STAGE_BYTES);
+          const uint64_t da = umma_desc_k_sw128(sa);
+          const uint64_t db = umma_desc_k_sw128(sa + C2_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc5_mma_f8_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc8, 1u);   // 32 B = 32 fp8 per UMMA
           tc5_commit_mc(&empty_bar[stage]);
           if (++stage == C2_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -275,11 +308,17 @@ gemm_tc5_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
 template <int KIND>
 static int launch_2cta(const GemmCall& g, cudaStream_t stream, int num_sms) {
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, ta8, tb8;
   const int Ka = g.awrap > 0 ? g.awrap : g.K;
   const int Kb = g.kwrap > 0 ? g.kwrap : g.K;
   if (make_tmap_k64(&ta, g.A, g.M, Ka, g.lda, C2_BM) != M5_OK) return M5_ERR_CUDA;
   if (make_tmap_k64(&tb, g.W, g.N, Kb, g.ldw, C2_BN / 2) != M5_OK) return M5_ERR_CUDA;
+  ta8 = ta; tb8 = tb;
+  if (g.A8) {
+    if (!g.W8 || g.K8 <= 0 || g.K8 % 128 != 0 || g.lda8 % 16 != 0 || g.ldw8 % 16 != 0) return M5_ERR_ARG;
+    if (make_tmap_u8_k128(&ta8, g.A8, g.M, g.K8, g.lda8, C2_BM) != M5_OK) return M5_ERR_CUDA;
+    if (make_tmap_u8_k128(&tb8, g.W8, g.N, g.K8, g.ldw8, C2_BN / 2) != M5_OK) return M5_ERR_CUDA;
+  }
   static DeviceOnce once;   // one per template instantiation
   unsigned long long bit;
   if (once.needed(bit)) {
@@ -292,8 +331,10 @@ static int launch_2cta(const GemmCall& g, cudaStream_t stream, int num_sms) {
   const int clusters = min(num_sms / 2, m_tiles * n_tiles);
   GemmEpi e;
   e.bias = g.bias; e.colscale = g.colscale; e.out = g.out; e.out_lo = g.out_lo; e.ldc = g.ldc;
+  e.out_lo8 = g.out_lo8; e.ldc8 = g.ldc8;
   e.mode = g.mode; e.act = g.act; e.accumulate = g.accumulate;
-  gemm_tc5_2cta_kernel<KIND><<<2 * clusters, C2_THREADS, C2_TOTAL, stream>>>(ta, tb, g.M, g.N, g.K, g.kwrap, g.awrap, e);
+  gemm_tc5_2cta_kernel<KIND><<<2 * clusters, C2_THREADS, C2_TOTAL, stream>>>(ta, tb, ta8, tb8, g.M, g.N, g.K, g.kwrap, g.awrap,
+                                                                               g.A8 ? g.K8 : 0, e);
   return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
 }
 
@@ -305,6 +346,7 @@ int gemm_tc5_2cta(const GemmCall& g, cudaStream_t stream, int num_sms) {
     case E_SWIGLU: return launch_2cta<E_SWIGLU>(g, stream, num_sms);
     case E_F16_SPLIT: return launch_2cta<E_F16_SPLIT>(g, stream, num_sms);
     case E_SWIGLU_SPLIT: return launch_2cta<E_SWIGLU_SPLIT>(g, stream, num_sms);
+    case E_SWIGLU_SPLIT8: return launch_2cta<E_SWIGLU_SPLIT8>(g, stream, num_sms);
     default: return launch_2cta<E_GENERIC>(g, stream, num_sms);
   }
 }

@@ -35,6 +35,8 @@ struct DecLayerW {
   const __half* ca_kv_w; const float* ca_kv_b;    // [2D, D]
   const __half* ca_out_w; const float* ca_out_b;
   const __half* wv; const __half* w2; const float* b2;
+  // optional e4m3 copies (x 2^+2) for the fp8 lo pass (mixed8): null when the tensor table has none
+  const uint8_t *sa_in_w8 = nullptr, *sa_out_w8 = nullptr, *ca_out_w8 = nullptr, *wv8 = nullptr, *w28 = nullptr;
 };
 int load_enc_layer(m5_ctx* ctx, const std::string& prefix, EncLayerW& w);
 int load_dec_layer(m5_ctx* ctx, const std::string& prefix, DecLayerW& w);
@@ -48,6 +50,9 @@ struct BlockScratch {
   __half* kv16 = nullptr;   // [mem_rows, 2*D] cross-attention keys/values
   __half* qkv16_lo = nullptr;  // [rows, 3*D]     low halves of q/k/v (precise mode)
   __half* kv16_lo = nullptr;   // [mem_rows, 2*D]
+  uint8_t* h8 = nullptr;       // [rows, D]   mixed8: e5m2 lo halves of the normalised activations
+  uint8_t* att8 = nullptr;     // [rows, D]   ... of the attention output
+  uint8_t* g8 = nullptr;       // [rows, ff]  ... of the gated FFN activations
 };
 size_t block_scratch_bytes(int rows, int mem_rows, int D, int ff);
 void block_scratch_carve(Arena& a, BlockScratch& s, int rows, int mem_rows, int D, int ff);
@@ -57,7 +62,10 @@ void block_scratch_carve(Arena& a, BlockScratch& s, int rows, int mem_rows, int 
 //   M5_NUM_PRECISE every activation operand is an fp16 (hi, lo) pair; attention in the 3-term mma.sync kernel
 //   M5_NUM_MIXED   GEMM activations, keys and values are (hi, lo) pairs, queries and probabilities single fp16; attention on
 //                  tcgen05 (split-KV kernel) -- the cheapest setting that holds 1e-3 max-abs on the logits
-enum { M5_NUM_FAST = 0, M5_NUM_PRECISE = 1, M5_NUM_MIXED = 2 };
+//   M5_NUM_MIXED8  like MIXED, but in the big decoder GEMMs the lo half of every activation pair is an e5m2 value (x 2^-2)
+//                  multiplied against an e4m3 copy of the weights (x 2^+2) by a kind::f8f6f4 UMMA pass into the same TMEM
+//                  accumulator: the correction term needs ~4 bits, the fp8 pass runs at twice the fp16 rate
+enum { M5_NUM_FAST = 0, M5_NUM_PRECISE = 1, M5_NUM_MIXED = 2, M5_NUM_MIXED8 = 3 };
 
 // x (fp32 [rows, D]) is updated in place.
 int encoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const EncLayerW& w, int D, int H, int ff, float eps,

@@ -43,8 +43,15 @@ struct GemmCall {
   int act = M5_ACT_NONE;
   int accumulate = 0;
   int force_bn = 0;
+  // fp8 "lo" pass (mixed8 numerics): after the K fp16 columns of A (the hi halves) the SAME accumulator receives
+  // A8[M, K8] (e5m2, the lo halves scaled by 2^-2) x W8[N, K8] (e4m3, the weights scaled by 2^+2) through
+  // tcgen05.mma kind::f8f6f4 at twice the fp16 rate.  CTA-pair kernel only (gemm_f8lo_eligible); K8 % 128 == 0.
+  const uint8_t* A8 = nullptr; const uint8_t* W8 = nullptr;
+  int K8 = 0, lda8 = 0, ldw8 = 0;   // row strides in bytes
+  uint8_t* out_lo8 = nullptr; int ldc8 = 0;   // SwiGLU pair output with the lo half as e5m2 (scaled 2^-2)
 };
 int gemm_tc5(const GemmCall& g, cudaStream_t stream, int num_sms);
+bool gemm_f8lo_eligible(int M, int N, int num_sms);   // does this shape run on the CTA-pair kernel?
 
 // ---- skinny (M <= 32) weight-streaming GEMM for the AR decode step (gemm_skinny.cu) ------------
 struct SkinnyCall {
@@ -73,6 +80,8 @@ struct NormCall {
   int rms = 0;
   __half* out = nullptr;
   __half* out_lo = nullptr;  // optional
+  uint8_t* out_lo8 = nullptr;  // optional: lo half as e5m2 scaled by 2^-2 (mixed8 numerics), row stride ldo8 bytes
+  int ldo8 = 0;
   float* out_f32 = nullptr;  // optional
   int ldo = 0;
   const int* row_map = nullptr;  // optional: output row i reads input row row_map[i]
@@ -96,6 +105,7 @@ struct AttnCall {
   int impl = 0;                // 0 auto, 1 mma.sync kernel, 2 tcgen05 kernel
   // split-precision mode (mma.sync kernel only): low halves of Q/K/V (same strides) and of the output
   const __half* Qlo = nullptr; const __half* Klo = nullptr; const __half* Vlo = nullptr; __half* Olo = nullptr;
+  uint8_t* Olo8 = nullptr; int ldo8 = 0;   // tcgen05 pair kernel: lo half of the output as e5m2 scaled by 2^-2 instead of fp16
 };
 int flash_attn(const AttnCall& c, cudaStream_t stream);      // mma.sync (causal prefill, tiny problems)
 int flash_attn_tc5(const AttnCall& c, cudaStream_t stream);  // tcgen05 / TMEM (attention_tc5.cu)

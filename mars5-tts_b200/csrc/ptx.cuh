@@ -169,6 +169,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
          | ((M >> 4) << 24);  // m_dim
 }
 
+// Instruction descriptor for kind::f8f6f4: A = e5m2 (format 1), B = e4m3 (format 0), fp32 accumulate, both K-major
+// (cute/arch/mma_sm100_desc.hpp InstrDescriptor / MXF8F6F4Format).
+__host__ __device__ constexpr uint32_t umma_idesc_e5m2_e4m3(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 7) | (0u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // ---------------------------------------------------------------- cp.async / ldmatrix / mma.sync
 M5_DEVINL void cp_async16(void* smem_dst, const void* gmem_src, bool pred) {
   uint32_t sz = pred ? 16u : 0u;

@@ -2,6 +2,8 @@
 // embedding gathers with sinusoidal position terms.  One warp per row, 128-bit loads, fp32 statistics.
 #include "m5_internal.h"
 #include "ptx.cuh"
+#include <cuda_fp8.h>
+
 #include "rowops.h"
 
 namespace m5 {
@@ -61,6 +63,11 @@ __global__ void __launch_bounds__(256) norm_rows_kernel(NormCall p) {
         __half2* ol = reinterpret_cast<__half2*>(p.out_lo + (size_t)row * p.ldo + i);
         ol[0] = __floats2half2_rn(y[0] - __half2float(h0), y[1] - __half2float(h1));
         ol[1] = __floats2half2_rn(y[2] - __half2float(h2), y[3] - __half2float(h3));
+      }
+      if (p.out_lo8) {
+        const __half hh[4] = {h0, h1, h2, h3};
+        for (int e = 0; e < 4; ++e)
+          p.out_lo8[(size_t)row * p.ldo8 + i + e] = (uint8_t)__nv_cvt_float_to_fp8((y[e] - __half2float(hh[e])) * 0.25f, __NV_SATFINITE, __NV_E5M2);
       }
     }
   }
@@ -123,6 +130,14 @@ __global__ void __launch_bounds__(256) norm_rows_reg_kernel(NormCall p) {
         const __half2 l0 = __floats2half2_rn(y[0] - __half2float(h0), y[1] - __half2float(h1));
         const __half2 l1 = __floats2half2_rn(y[2] - __half2float(h2), y[3] - __half2float(h3));
         *reinterpret_cast<uint2*>(p.out_lo + (size_t)row * p.ldo + i) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+      }
+      if (p.out_lo8) {   // lo halves as e5m2 scaled by 2^-2 (mixed8 numerics: the fp8 pass of the consuming GEMM)
+        const __half hh[4] = {h0, h1, h2, h3};
+        uint32_t w = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          w |= (uint32_t)__nv_cvt_float_to_fp8((y[e] - __half2float(hh[e])) * 0.25f, __NV_SATFINITE, __NV_E5M2) << (8 * e);
+        *reinterpret_cast<uint32_t*>(p.out_lo8 + (size_t)row * p.ldo8 + i) = w;
       }
     }
   }

@@ -21,7 +21,7 @@ def _flatten(tensors):
 def _unflatten(blob, manifest):
     out = {}
     for k, dt, shape, o, n in manifest:
-        dtype = {"torch.float16": torch.float16, "torch.float32": torch.float32}[dt]
+        dtype = {"torch.float16": torch.float16, "torch.float32": torch.float32, "torch.uint8": torch.uint8}[dt]
         out[k] = blob[o:o + n].view(dtype).reshape(shape)
     return out
 

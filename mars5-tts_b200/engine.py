@@ -85,7 +85,7 @@ class Engine:
             nm = k.encode()
             self._names.append(nm)
             arr[i].name, arr[i].ptr, arr[i].numel = nm, v.data_ptr(), v.numel()
-            arr[i].dtype = capi.DT_F16 if v.dtype == torch.float16 else capi.DT_F32
+            arr[i].dtype = capi.DT_F16 if v.dtype == torch.float16 else (capi.DT_U8 if v.dtype == torch.uint8 else capi.DT_F32)
         self.ctx = C.c_void_p()
         rc = self.lib.m5_create(self.device, C.byref(self.cfg), arr, len(self.tensors), C.byref(self.ctx))
         if rc != 0:

@@ -150,6 +150,11 @@ def repack(ar_sd, nar_sd, voc_sd, dims, max_pos=4096, n_t=1000):
         t[p + "ca_out_w"], t[p + "ca_out_b"] = nar_sd[s + "multihead_attn.out_proj.weight"].half(), nar_sd[s + "multihead_attn.out_proj.bias"].float()
         t[p + "wv"] = _interleave(nar_sd[s + "activation.W.weight"], nar_sd[s + "activation.V.weight"]).half()
         t[p + "w2"], t[p + "b2"] = nar_sd[s + "linear2.weight"].half(), nar_sd[s + "linear2.bias"].float()
+        # e4m3 copies scaled by 2^+2 for the fp8 lo pass of the `mixed8` numerics: the product with
+        # the e5m2 lo halves (scaled by 2^-2) lands at true scale in the fp16 pass's TMEM accumulator
+        if hasattr(torch, "float8_e4m3fn") and t[p + "wv"].device.type != "meta":
+            for nm in ("sa_in_w", "sa_out_w", "ca_out_w", "wv", "w2"):
+                t[p + nm + "8"] = (t[p + nm].float() * 4.0).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
     t["nar.dec.norm_w"], t["nar.dec.norm_b"] = nar_sd["tfm.decoder.norm.weight"].float(), nar_sd["tfm.decoder.norm.bias"].float()
     for nm, src in (("t_enc", "timestep_encoder_emb"), ("t_dec", "timestep_decoder_emb")):
         t[f"nar.{nm}.w0"], t[f"nar.{nm}.b0"] = nar_sd[src + ".0.weight"].half(), nar_sd[src + ".0.bias"].float()

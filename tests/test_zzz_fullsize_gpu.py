@@ -195,12 +195,13 @@ def test_nar_forward_full_dims_absolute_tolerance(full_engine):
         ref = nar_oracle.nar_forward(nar_sd, cfg, text, codes, x, t, drop_cond=drop).numpy()
         scale = float(np.abs(ref).max())
         errs = {}
-        for name, mode in (("fast", cp.NUM_FAST), ("mixed", cp.NUM_MIXED), ("precise", cp.NUM_PRECISE)):
+        for name, mode in (("fast", cp.NUM_FAST), ("mixed", cp.NUM_MIXED), ("mixed8", cp.NUM_MIXED8), ("precise", cp.NUM_PRECISE)):
             got = eng.nar_forward([text.numpy()], [codes.numpy()], [x.numpy()], t, drop_cond=drop, precise=mode)[0]
             errs[name] = float(np.abs(got - ref).max())
         print(f"NAR logits at full dims (S={S}, drop_cond={drop}): max|logit| {scale:.2f}; max-abs error " +
               ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
         assert errs["mixed"] < 1e-3, errs
+        assert errs["mixed8"] < 1e-3, errs
         assert errs["precise"] < 1e-3, errs
         assert errs["fast"] < 1e-3 * max(1.0, scale), errs
 
@@ -259,10 +260,35 @@ def test_nar_infer_full_dims_code_agreement(full_engine):
     codes = [torch.randint(0, 1024, (Pf, 8), generator=g).numpy().astype(np.int32) for _ in range(B)]
     l0 = [torch.randint(0, 1024, (N,), generator=g).numpy().astype(np.int32) for _ in range(B)]
     out = {}
-    for name, mode in (("precise", cp.NUM_PRECISE), ("mixed", cp.NUM_MIXED), ("fast", cp.NUM_FAST)):
+    for name, mode in (("precise", cp.NUM_PRECISE), ("mixed", cp.NUM_MIXED), ("mixed8", cp.NUM_MIXED8), ("fast", cp.NUM_FAST)):
         ncfg = eng.make_nar_cfg(InferenceConfig(), T=20, precise=mode)
         out[name] = np.stack(eng.nar_infer(texts, codes, l0, ncfg, seed=5, utt_ids=[100, 101]))
-    mm = {k: float((out[k] != out["precise"]).mean()) for k in ("mixed", "fast")}
-    print(f"NAR codes after T=20 at full dims vs precise: mixed {mm['mixed']:.4%} differ, fast {mm['fast']:.4%} differ")
+    mm = {k: float((out[k] != out["precise"]).mean()) for k in ("mixed", "mixed8", "fast")}
+    print(f"NAR codes after T=20 at full dims vs precise: mixed {mm['mixed']:.4%} differ, mixed8 {mm['mixed8']:.4%}, fast {mm['fast']:.4%} differ")
     assert mm["mixed"] <= 0.02, mm
     assert mm["mixed"] <= mm["fast"] + 1e-9 or mm["fast"] < 0.02, mm
+
+
+def test_gemm_fp8_lo_pass(m5lib, bare_ctx):
+    """mixed8: C = A_hi W^T (fp16 UMMA) + A_lo8 W8^T (kind::f8f6f4 UMMA, e5m2 x e4m3, scales 2^-2 x 2^+2) in ONE TMEM
+    accumulator.  Against the fp32 product of the unrounded A the result must be an order of magnitude closer than the
+    fp16-only product, and close to the fp16-pair product it replaces."""
+    M, N, K = 40960, 3072, 1024
+    g = torch.Generator(device=DEV).manual_seed(71)
+    A32 = torch.randn(M, K, device=DEV, generator=g)
+    W = (torch.randn(N, K, device=DEV, generator=g) * 0.03).half()
+    Ah = A32.half()
+    lo = A32 - Ah.float()
+    A8 = (lo * 0.25).to(torch.float8_e5m2).view(torch.uint8).contiguous()
+    W8 = (W.float() * 4.0).to(torch.float8_e4m3fn).view(torch.uint8).contiguous()
+    out = torch.zeros(M, N, device=DEV)
+    rc = m5lib.m5_dbg_gemm_f8lo(bare_ctx, ptr(Ah), K, ptr(A8), ptr(W), ptr(W8), M, N, K, ptr(out), N)
+    capi.check(bare_ctx, rc, "gemm_f8lo")
+    _sync(m5lib, bare_ctx)
+    e8 = e16 = 0.0
+    for r0 in range(0, M, 8192):
+        ref = A32[r0:r0 + 8192] @ W.float().T
+        e8 = max(e8, (out[r0:r0 + 8192] - ref).abs().max().item())
+        e16 = max(e16, (Ah[r0:r0 + 8192].float() @ W.float().T - ref).abs().max().item())
+    print(f"fp8 lo pass: max-abs {e8:.2e} vs fp32 (fp16-only operands: {e16:.2e})")
+    assert e8 < 0.2 * e16, (e8, e16)
