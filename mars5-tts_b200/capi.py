@@ -105,10 +105,15 @@ def load(path=None):
 
 
 def ptr(t):
-    """Raw pointer of a torch tensor / numpy array / None."""
+    """Raw pointer of a torch tensor / numpy array / None.  A CUDA tensor was produced on torch's current stream and is
+    about to be consumed on the context's own (non-blocking) stream: torch's stream is drained before the address is handed
+    out, so that no C-ABI call can overtake the kernels that fill its inputs."""
     if t is None:
         return None
     if hasattr(t, "data_ptr"):
+        if getattr(t, "is_cuda", False):
+            import torch
+            torch.cuda.current_stream(t.device).synchronize()
         return C.c_void_p(t.data_ptr())
     if hasattr(t, "ctypes"):
         return C.c_void_p(t.ctypes.data)

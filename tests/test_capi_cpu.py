@@ -47,8 +47,9 @@ def test_struct_sizes_match_header_layout(tmp_path):
 
 
 def test_built_for_sm100a_with_tcgen05_and_tma():
-    """The shipped SASS contains the Blackwell instructions the design claims (UTCHMMA = tcgen05.mma, UTMALDG = TMA, LDTM)."""
+    """The shipped SASS contains the Blackwell instructions the design claims (UTCHMMA = tcgen05.mma kind::f16, UTCQMMA = kind::f8f6f4 -- the
+    fp8 lo pass of the mixed8 numerics --, .2CTA = cta_group::2, UTMALDG = TMA, LDTM = tcgen05.ld, LDGSTS = cp.async of the decode kernel's weight ring)."""
     out = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out or "SM100a" in out.upper() or "sm_100" in out
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "UTCQMMA.2CTA", "UTMALDG.2D", "LDTM", "LDGSTS"):
         assert mnemonic in out, mnemonic
