@@ -583,7 +583,7 @@ def main():
     roofline_ar = None
     if ap_["launches"] > 0:
         gbs = ap_["bytes"] / max(ap_["ms"], 1e-9) / 1e6
-        roofline_ar = {"kernel": "ar_decode_kernel (one persistent cooperative kernel per decode step, all 26 layers + vocabulary projection) + ar_sample_kernel", "bound": "hbm",
+        roofline_ar = {"kernel": "ar_decode_kernel (one persistent cooperative kernel per decode step: all 26 layers, vocabulary projection, categorical sampler)", "bound": "hbm",
                        "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
                        "bytes_per_step": ap_["bytes"] / ap_["launches"], "ms_per_decode_step": ap_["ms"] / ap_["launches"],
                        "decode_steps": ap_["launches"], "share_of_step": ap_["ms"] / ms,

@@ -91,7 +91,7 @@ def load(path=None):
     global _lib
     if _lib is not None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("M5_LIB_PATH") or LIB_PATH   # M5_LIB_PATH: an alternative build of the same ABI (tools/ A/B runs)
     if not os.path.exists(path):
         raise RuntimeError(f"{path} not found: run `python -c 'import __graft_entry__ as g; g.build()'` first. "
                            "There is no CPU/PyTorch fallback for the MARS5 hot path.")

@@ -490,11 +490,18 @@ int m5_ar_generate(m5_ctx* ctx, int32_t B, const int32_t* prompt_ids, const int3
       rc = ar_decode_step(ctx, w, B, st, kc, vc, Wc, sc);
     } else {
       g_use_pdl = false;
+      // the sampler is the kernel's last phase (one launch per decode step); M5_AR_SAMPLE_SEPARATE=1 keeps it a kernel of
+      // its own behind the decode kernel (debugging aid)
+      static const bool sample_separate = getenv("M5_AR_SAMPLE_SEPARATE") != nullptr;
+      dp.fuse_sample = (!sample_separate && ar_decode_can_fuse_sampler(V, cfg->top_k)) ? 1 : 0;
+      dp.sample = sc;   // sc.cap was filled by the prefill's ar_sample call above
       rc = ar_decode_launch(dp, ctx->num_sms, ctx->stream);
       if (rc != M5_OK) ctx->fail(rc, std::string("ar_decode_launch failed: ") + cudaGetErrorString(cudaGetLastError()));
       ctx->launches++;
-      if (rc == M5_OK && ar_sample(sc, ctx->stream) != M5_OK) rc = ctx->fail(M5_ERR_CUDA, "ar_sample failed");
-      ctx->launches++;
+      if (!dp.fuse_sample) {
+        if (rc == M5_OK && ar_sample(sc, ctx->stream) != M5_OK) rc = ctx->fail(M5_ERR_CUDA, "ar_sample failed");
+        ctx->launches++;
+      }
     }
     g_use_pdl = false;
     cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);

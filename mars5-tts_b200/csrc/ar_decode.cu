@@ -25,6 +25,7 @@
 #include <cuda.h>
 
 #include "ar_decode.h"
+#include "sampler_body.cuh"
 #include "ptx.cuh"
 
 namespace m5 {
@@ -39,6 +40,7 @@ static constexpr int AD_AWARPS = 6;      // warps of a CTA that run attention it
 static constexpr int AD_STAGE_BYTES = 2 * AD_KT * 128;                      // K tile + V tile
 static constexpr int AD_PART = 68;       // floats per split partial: m, l, pad, pad, acc[64] (16-byte aligned rows)
 static constexpr int AD_SMEM_KV = AD_AWARPS * AD_NST * AD_STAGE_BYTES;       // 192 KB (the GEMM phases alias it: W staging + X)
+static constexpr int AD_RED = 4;        // split-K partials the reducing CTA keeps in flight per round (16 measured slower: profiles/r2_ar_decode_timeline.txt)
 static constexpr int AD_MAX_KSLICE = 896;                                    // activation slice: 32 rows x (2 * 896 + 64) B = 58 KB
 static_assert(AD_W_BYTES + 32 * (AD_MAX_KSLICE * 2 + 64) <= AD_SMEM_KV, "weight staging + activation slice must fit the KV ring region");
 static constexpr int AD_SMEM = AD_SMEM_KV + 1024;                            // + mbarriers, tickets
@@ -227,14 +229,14 @@ M5_DEVINL void gemm_phase(const ArDecodeParams& p, const ArGemm& g, const float*
         const int n = nrow0 + 2 * pr;
         if (b >= p.B || n + 1 >= g.N) continue;
         float a = 0.f, c = 0.f;
-        for (int s0 = 0; s0 < g.ksplit; s0 += 4) {   // 4 slices' loads in flight, summed in slice order (deterministic)
-          float2 v2[4];
+        for (int s0 = 0; s0 < g.ksplit; s0 += AD_RED) {   // AD_RED slices' loads in flight, summed in slice order (deterministic)
+          float2 v2[AD_RED];
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
+          for (int e = 0; e < AD_RED; ++e)
             v2[e] = (s0 + e < g.ksplit) ? __ldcg(reinterpret_cast<const float2*>(base + (size_t)(s0 + e) * (32 * AD_ROWS) + (size_t)b * AD_ROWS + 2 * pr))
                                         : make_float2(0.f, 0.f);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { a += v2[e].x; c += v2[e].y; }
+          for (int e = 0; e < AD_RED; ++e) { a += v2[e].x; c += v2[e].y; }
         }
         p.g16[(size_t)b * (g.N / 2) + (n >> 1)] = __float2half_rn((a / (1.f + __expf(-a))) * c);
       }
@@ -248,14 +250,14 @@ M5_DEVINL void gemm_phase(const ArDecodeParams& p, const ArGemm& g, const float*
             r_pre = __ldcg(reinterpret_cast<const float4*>(out_f32 + (size_t)b * ldo + nrow0 + 4 * lane));
         }
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s0 = 0; s0 < g.ksplit; s0 += 4) {   // 4 slices' loads in flight, summed in slice order (deterministic)
-          float4 q[4];
+        for (int s0 = 0; s0 < g.ksplit; s0 += AD_RED) {   // AD_RED slices' loads in flight, summed in slice order (deterministic)
+          float4 q[AD_RED];
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
+          for (int e = 0; e < AD_RED; ++e)
             q[e] = (s0 + e < g.ksplit) ? __ldcg(reinterpret_cast<const float4*>(base + (size_t)(s0 + e) * (32 * AD_ROWS) + (size_t)b * AD_ROWS + 4 * lane))
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { v.x += q[e].x; v.y += q[e].y; v.z += q[e].z; v.w += q[e].w; }
+          for (int e = 0; e < AD_RED; ++e) { v.x += q[e].x; v.y += q[e].y; v.z += q[e].z; v.w += q[e].w; }
         }
         const int n = nrow0 + 4 * lane;
         float* o = out_f32 + (size_t)b * ldo + n;
@@ -561,7 +563,8 @@ M5_DEVINL void attn_phase(const ArDecodeParams& p, const ArLayerDev& lw, const C
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int NT>
 __global__ void __launch_bounds__(AD_THREADS, 1)
-ar_decode_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v, ArDecodeParams p) {
+ar_decode_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                 const __grid_constant__ ArDecodeParams p) {
   extern __shared__ __align__(1024) uint8_t ad_smem[];
   uint8_t* smem = ad_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -649,6 +652,11 @@ ar_decode_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_consta
   // ---- logits = Wout . rmsnorm(x)
   gemm_phase<NT, X_NORM, EPI_STORE>(p, p.g_out, p.final_norm, p.logits, p.V, smem, (int)blockIdx.x < p.g_out.tiles * p.g_out.ksplit);
   if (pf && blockIdx.x == 0 && tid == 0) pf[0] = pf[1] = global_timer_ns();
+  // ---- sampler (ar_generate.py:73-135): warp the logits of row b, draw the token, append it / stop the row
+  if (p.fuse_sample) {
+    grid_sync(p.gbar, epoch, nullptr);
+    if ((int)blockIdx.x < p.B) ar_sample_row(p.sample, blockIdx.x, smem);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -723,6 +731,11 @@ static int ad_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
              ? M5_OK : M5_ERR_CUDA;
+}
+
+bool ar_decode_can_fuse_sampler(int V, int top_k) {
+  static_assert(SP_THREADS == AD_THREADS, "the sampler phase runs on the decode kernel's CTA");
+  return sample_smem_bytes(V, sample_cap(V, top_k)) <= (size_t)AD_SMEM_KV;
 }
 
 int ar_decode_launch(const ArDecodeParams& p, int num_sms, cudaStream_t stream) {

@@ -3,6 +3,7 @@
 #include <algorithm>
 
 #include "m5_internal.h"
+#include "sampler.h"
 
 namespace m5 {
 
@@ -43,6 +44,10 @@ struct ArDecodeParams {
   unsigned* gbar = nullptr;  // device-wide barrier counter
   unsigned long long* prof = nullptr;   // optional [1 + 5 * n_layers][2] globaltimer stamps of CTA 0 (work done, barrier passed)
   ArGemm g_qkv, g_wo, g_w13, g_w2, g_out;   // g_out.W = vocabulary projection
+  // last phase: the categorical sampler of the step (sampler_body.cuh), CTA b = row b, after one more device-wide barrier.
+  // fuse_sample = 0: the caller launches ar_sample_kernel behind this kernel instead.
+  int fuse_sample = 0;
+  SampleCall sample;
 };
 
 int ar_decode_plan(ArDecodeParams& p, int num_sms);          // fills the ArGemm splits and ssq_tiles
@@ -51,6 +56,7 @@ int ar_decode_max_tiles(const ArDecodeParams& p);
 int ar_decode_split_keys(int B, int H, int max_kv, int num_sms);
 int ar_decode_splits_for(int max_kv, int split_keys);
 size_t ar_decode_attn_floats(int B, int H, int n_split);
+bool ar_decode_can_fuse_sampler(int V, int top_k);           // the sampler's shared-memory working set fits the kernel's
 int ar_decode_launch(const ArDecodeParams& p, int num_sms, cudaStream_t stream);   // memset(gbar) + cooperative launch
 
 }  // namespace m5

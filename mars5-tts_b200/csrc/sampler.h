@@ -34,6 +34,8 @@ struct SampleCall {
   int cap = 0;             // filled by ar_sample
 };
 int ar_sample(SampleCall& c, cudaStream_t stream);
+int sample_cap(int V, int top_k);              // survivor slots the sort works on
+size_t sample_smem_bytes(int V, int cap);      // dynamic shared memory of one sampler CTA
 
 // NAR posterior + sampling (posterior.cu): one warp per (row, codebook).
 struct PosteriorCall {

@@ -30,7 +30,11 @@ eos = eng.dims["ar_vocab"] - 1
 acfg = eng.make_ar_cfg(InferenceConfig(), args.P + args.N + 2, eos, force_len=args.N + 8, sync_every=64)  # rows still running at the last step: its profile is a normal step
 peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
     os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6569.6
-for rep in range(3):
+from bench import ClockSampler  # noqa: E402  (nvidia-smi clock samples during the decode loops)
+ap_reps = int(os.environ.get("M5_AR_BENCH_REPS", "3"))
+for rep in range(ap_reps):
+    cs = ClockSampler(0)
+    cs.start()
     eng.lib.m5_profile_enable(eng.ctx, 1)
     ids, _, _ = eng.ar_generate(prompts, spk, [500] * args.B, acfg, seed=rep)
     a, b, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
@@ -38,4 +42,4 @@ for rep in range(3):
     eng.lib.m5_profile_enable(eng.ctx, 0)
     gbs = c.value / max(a.value, 1e-9) / 1e6
     print(f"rep {rep}: {n.value} decode steps, {a.value / max(n.value, 1):.3f} ms/step, {c.value / max(n.value, 1) / 1e9:.2f} GB/step algorithmic, "
-          f"{gbs:.0f} GB/s = {gbs / peak:.3f} of {peak:.0f}; generated {len(ids[0]) - args.P} tokens", flush=True)
+          f"{gbs:.0f} GB/s = {gbs / peak:.3f} of {peak:.0f}; generated {len(ids[0]) - args.P} tokens; clocks {cs.stop()}", flush=True)
