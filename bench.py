@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 METRIC = "audio sec/s synthesized (deep-clone, batch 32)"
 UNIT = "audio_s/s"
 BUDGET_S = float(os.environ.get("M5_BENCH_BUDGET_S", "780"))
-MODES = {"fast": 0, "precise": 1, "mixed": 2, "mixed8": 3}
+MODES = {"fast": 0, "precise": 1, "mixed": 2, "mixed8": 3, "mixed8k": 4}
 
 
 def elapsed():
@@ -389,10 +389,11 @@ def main():
                     help="BASELINE configs: c2 = deep B=1 50 tok; c3 = deep B=32 100 tok (headline); c4 = mixed lengths; c5 = NAR-only sweep")
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--T", type=int, default=0)
-    ap.add_argument("--mode", default=os.environ.get("M5_BENCH_MODE", "mixed8"), choices=list(MODES),
+    ap.add_argument("--mode", default=os.environ.get("M5_BENCH_MODE", ""), choices=[""] + list(MODES),
                     help="NAR numerics: fast = fp16 operands everywhere (fails the 1e-3 bound); mixed = (hi, lo) fp16 pairs for the GEMM "
-                         "activations, K and V; mixed8 = mixed with the lo pass of the big decoder GEMMs in fp8 (default: both hold "
-                         "1e-3 max-abs on the logits, tests/test_zzz_fullsize_gpu.py); precise = everything split")
+                         "activations, K and V; mixed8 = mixed with the lo pass of the big decoder GEMMs in fp8; mixed8k = mixed8 with "
+                         "single-fp16 keys in the decoder self-attention (all three hold 1e-3 max-abs on the logits, "
+                         "tests/test_zzz_fullsize_gpu.py); precise = everything split.  Default: capi.NUM_DEFAULT, what Mars5TTS runs")
     ap.add_argument("--precise", type=int, default=-1, help="deprecated alias: 0 = fast, 1 = precise")
     ap.add_argument("--ntok", type=int, default=0, help="profiling aid: override the target-text token count (N = 15 * ntok)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -403,6 +404,9 @@ def main():
     args = ap.parse_args()
     if args.precise >= 0:
         args.mode = "precise" if args.precise else "fast"
+    if not args.mode:
+        from mars5_tts_b200 import capi as _capi
+        args.mode = {v: k for k, v in MODES.items()}[_capi.NUM_DEFAULT]
     mode = MODES[args.mode]
 
     from mars5_tts_b200 import synth

@@ -123,7 +123,9 @@ typedef struct {
                        *                           single fp16, attention on tcgen05: the cheapest setting that keeps the
                        *                           logits within 1e-3 max-abs of the fp32 reference
                        *               3 mixed8  = mixed, with the lo half of the big decoder GEMMs' activation pairs as an
-                       *                           fp8 (e5m2 x e4m3) tcgen05 pass into the same accumulator */
+                       *                           fp8 (e5m2 x e4m3) tcgen05 pass into the same accumulator
+                       *               4 mixed8k = mixed8, with the keys of the decoder self-attention as single fp16 values
+                       *                           (values stay pairs): one S = Q K^T pass instead of two */
   /* optional HOST tables [4][T]: log_alpha, log_1_min_alpha, log_cumprod_alpha, log_1_min_cumprod_alpha
    * (MultinomialDiffusion.__init__, diffuser.py:76-95); NULL -> computed inside the library */
   const float* schedule;
@@ -232,7 +234,8 @@ int m5_dbg_attn(m5_ctx* ctx, const void* Q, const void* K, const void* V, int32_
                 void* O, int32_t ldo, int32_t n_heads, int32_t n_seqs, int32_t max_q, const int32_t* q_start,
                 const int32_t* q_len, const int32_t* k_start, const int32_t* k_len, int32_t causal, int32_t impl,
                 int32_t q_rows, int32_t k_rows); /* impl: 1 = mma.sync kernel, 2 = tcgen05 kernel (needs q_rows/k_rows) */
-/* tcgen05 kernel with keys / values as fp16 (hi, lo) pairs and the output written as a pair ("mixed" numerics). */
+/* tcgen05 kernel with keys / values as fp16 (hi, lo) pairs and the output written as a pair ("mixed" numerics).
+ * Klo == NULL: the keys are single fp16 values, only the values are pairs ("mixed8k"). */
 int m5_dbg_attn_split(m5_ctx* ctx, const void* Q, const void* K, const void* V, const void* Klo, const void* Vlo,
                       int32_t ldq, int32_t ldk, int32_t ldv, void* O, void* Olo, int32_t ldo, int32_t n_heads,
                       int32_t n_seqs, int32_t max_q, const int32_t* q_start, const int32_t* q_len, const int32_t* k_start,

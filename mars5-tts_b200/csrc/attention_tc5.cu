@@ -38,14 +38,17 @@ static constexpr int AT_KV_BYTES = AT_BK * AT_HD * 2;    //  8 KB
 static constexpr int AT_P_BYTES = AT_BQ * AT_BK * 2;     // 16 KB (one 128-row K-major block)
 static constexpr int AT_TMEM_COLS = 256, AT_TMEM_O = AT_SST * AT_BK;   // S slots at 0/64/128, O at 192
 static_assert(AT_TMEM_O + AT_HD <= AT_TMEM_COLS, "TMEM budget");
-// SPLIT = keys and values arrive as fp16 (hi, lo) pairs ("mixed" NAR numerics): every ring stage holds the
-// hi tile followed by the lo tile, S_j = Q K_hi^T + Q K_lo^T and O += P V_hi + P V_lo accumulate in the same TMEM columns,
-// and O is written as a (hi, lo) pair.  The rings are shallower (2 + 2 stages of 16 KB) so that two CTAs still fit one SM.
-template <bool SPLIT>
+// SPLIT = values (and, with KPAIR, keys) arrive as fp16 (hi, lo) pairs ("mixed" NAR numerics): a ring stage
+// holds the hi tile followed by the lo tile, S_j = Q K_hi^T + Q K_lo^T and O += P V_hi + P V_lo accumulate in the same TMEM
+// columns, and O is written as a (hi, lo) pair.  The rings are shallower (2 stages of 16 KB) so that two CTAs still fit one SM.
+// SPLIT && !KPAIR ("mixed8k"): keys are single fp16 values -- one S pass instead of two, 4 K stages of 8 KB; their rounding is
+// averaged over the ~2k keys of a decoder sequence (tools/precision_budget_mixed8.py: 1.3e-5 rms on the logits).
+template <bool SPLIT, bool KPAIR>
 struct AtCfg {
-  static constexpr int KST = SPLIT ? 2 : 4, VST = SPLIT ? 2 : 3;        // K ring, V ring
-  static constexpr int STAGE = SPLIT ? 2 * AT_KV_BYTES : AT_KV_BYTES;
-  static constexpr int OFF_Q = 0, OFF_K = AT_Q_BYTES, OFF_V = OFF_K + KST * STAGE, OFF_P = OFF_V + VST * STAGE,
+  static_assert(SPLIT || !KPAIR, "key pairs only together with value pairs");
+  static constexpr int KST = KPAIR ? 2 : 4, VST = SPLIT ? 2 : 3;        // K ring, V ring
+  static constexpr int KSTAGE = KPAIR ? 2 * AT_KV_BYTES : AT_KV_BYTES, VSTAGE = SPLIT ? 2 * AT_KV_BYTES : AT_KV_BYTES;
+  static constexpr int OFF_Q = 0, OFF_K = AT_Q_BYTES, OFF_V = OFF_K + KST * KSTAGE, OFF_P = OFF_V + VST * VSTAGE,
                        OFF_BAR = OFF_P + 2 * AT_P_BYTES;
   static constexpr int SMEM = OFF_BAR + 256;
   // mbarrier slots
@@ -145,13 +148,13 @@ struct Ring {
   }
 };
 
-template <bool SPLIT>
+template <bool SPLIT, bool KPAIR>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 flash_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_klo,
                  const __grid_constant__ CUtensorMap tmap_vlo, AttnTc5Params p) {
-  using C = AtCfg<SPLIT>;
-  constexpr int AT_KST = C::KST, AT_VST = C::VST, AT_STAGE = C::STAGE;
+  using C = AtCfg<SPLIT, KPAIR>;
+  constexpr int AT_KST = C::KST, AT_VST = C::VST, AT_KSTAGE = C::KSTAGE, AT_VSTAGE = C::VSTAGE;
   constexpr int AT_OFF_Q = C::OFF_Q, AT_OFF_K = C::OFF_K, AT_OFF_V = C::OFF_V, AT_OFF_P = C::OFF_P, AT_OFF_BAR = C::OFF_BAR;
   constexpr int B_QFULL = C::B_QFULL, B_KFULL = C::B_KFULL, B_KFREE = C::B_KFREE, B_VFULL = C::B_VFULL, B_VFREE = C::B_VFREE,
                 B_SREADY = C::B_SREADY, B_PREADY = C::B_PREADY, B_PVDONE = C::B_PVDONE, B_COUNT = C::B_COUNT;
@@ -192,19 +195,19 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int i = 0; i < n_tiles + AT_KLEAD; ++i) {
         if (i < n_tiles) {
           mbar_wait(bar + B_KFREE + kr.slot, kr.phase ^ 1);
-          mbar_arrive_expect_tx(bar + B_KFULL + kr.slot, AT_STAGE);
-          tma_load_2d(smem + AT_OFF_K + kr.slot * AT_STAGE, &tmap_k, bar + B_KFULL + kr.slot, head * AT_HD, krow + i * AT_BK);
-          if (SPLIT)
-            tma_load_2d(smem + AT_OFF_K + kr.slot * AT_STAGE + AT_KV_BYTES, &tmap_klo, bar + B_KFULL + kr.slot, head * AT_HD, krow + i * AT_BK);
+          mbar_arrive_expect_tx(bar + B_KFULL + kr.slot, AT_KSTAGE);
+          tma_load_2d(smem + AT_OFF_K + kr.slot * AT_KSTAGE, &tmap_k, bar + B_KFULL + kr.slot, head * AT_HD, krow + i * AT_BK);
+          if (KPAIR)
+            tma_load_2d(smem + AT_OFF_K + kr.slot * AT_KSTAGE + AT_KV_BYTES, &tmap_klo, bar + B_KFULL + kr.slot, head * AT_HD, krow + i * AT_BK);
           kr.next(AT_KST);
         }
         if (i >= AT_KLEAD) {
           mbar_wait(bar + B_VFREE + vr.slot, vr.phase ^ 1);
-          mbar_arrive_expect_tx(bar + B_VFULL + vr.slot, AT_STAGE);
-          tma_load_2d(smem + AT_OFF_V + vr.slot * AT_STAGE, &tmap_v, bar + B_VFULL + vr.slot, head * AT_HD,
+          mbar_arrive_expect_tx(bar + B_VFULL + vr.slot, AT_VSTAGE);
+          tma_load_2d(smem + AT_OFF_V + vr.slot * AT_VSTAGE, &tmap_v, bar + B_VFULL + vr.slot, head * AT_HD,
                       krow + (i - AT_KLEAD) * AT_BK);
           if (SPLIT)
-            tma_load_2d(smem + AT_OFF_V + vr.slot * AT_STAGE + AT_KV_BYTES, &tmap_vlo, bar + B_VFULL + vr.slot, head * AT_HD,
+            tma_load_2d(smem + AT_OFF_V + vr.slot * AT_VSTAGE + AT_KV_BYTES, &tmap_vlo, bar + B_VFULL + vr.slot, head * AT_HD,
                         krow + (i - AT_KLEAD) * AT_BK);
           vr.next(AT_VST);
         }
@@ -219,10 +222,10 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       auto issue_s = [&]() {
         mbar_wait(bar + B_KFULL + kr.slot, kr.phase);
         tc5_fence_after();
-        const uint64_t dk = umma_desc_k_sw128(smem_u32(smem + AT_OFF_K + kr.slot * AT_STAGE));
+        const uint64_t dk = umma_desc_k_sw128(smem_u32(smem + AT_OFF_K + kr.slot * AT_KSTAGE));
 #pragma unroll
         for (int k = 0; k < AT_HD / 16; ++k) tc5_mma_f16(tmem_base + sr.slot * AT_BK, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        if (SPLIT) {   // + Q K_lo^T: the lo tile sits AT_KV_BYTES behind the hi tile of the stage
+        if (KPAIR) {   // + Q K_lo^T: the lo tile sits AT_KV_BYTES behind the hi tile of the stage
           const uint64_t dkl = dk + (uint64_t)(AT_KV_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < AT_HD / 16; ++k) tc5_mma_f16(tmem_base + sr.slot * AT_BK, dq + 2 * k, dkl + 2 * k, idesc_s, 1);
@@ -242,7 +245,7 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         mbar_wait(bar + B_VFULL + vr.slot, vr.phase);
         tc5_fence_after();
         const uint64_t dp = umma_desc_k_sw128(smem_u32(smem + AT_OFF_P + pr.slot * AT_P_BYTES));
-        const uint64_t dv = umma_desc_mn_sw128(smem_u32(smem + AT_OFF_V + vr.slot * AT_STAGE));
+        const uint64_t dv = umma_desc_mn_sw128(smem_u32(smem + AT_OFF_V + vr.slot * AT_VSTAGE));
 #pragma unroll
         for (int k = 0; k < AT_BK / 16; ++k)   // A: 16 keys = 32 B inside the 128-byte P row; B: 16 key rows = 2048 B of V
           tc5_mma_f16(tmem_o, dp + 2 * k, dv + (uint64_t)(k * (16 * 128 >> 4)), idesc_o, (j != 0) || (k != 0));
@@ -417,20 +420,22 @@ int flash_attn_tc5(const AttnCall& c, cudaStream_t stream) {
   if (c.n_seqs <= 0 || c.max_q <= 0) return M5_OK;
   if (c.causal || c.q_rows <= 0 || c.k_rows <= 0) return M5_ERR_ARG;
   if ((c.ldq | c.ldk | c.ldv | c.ldo) % 8 != 0) return M5_ERR_ARG;
-  const bool split = c.Klo != nullptr;   // keys / values as (hi, lo) pairs, O written as a pair; Q and P stay single fp16
-  if (split && (!c.Vlo || !(c.Olo || c.Olo8))) return M5_ERR_ARG;
+  const bool split = c.Vlo != nullptr;   // values (and keys, when Klo is given) as (hi, lo) pairs, O written as a pair; Q and P stay single fp16
+  const bool kpair = split && c.Klo != nullptr;
+  if ((split && !(c.Olo || c.Olo8)) || (c.Klo && !c.Vlo)) return M5_ERR_ARG;
   CUtensorMap tq, tk, tv, tkl, tvl;
   const uint64_t cols = (uint64_t)c.n_heads * AT_HD;
   if (at_tmap(&tq, c.Q, c.q_rows, cols, c.ldq, AT_BQ) != M5_OK) return M5_ERR_CUDA;
   if (at_tmap(&tk, c.K, c.k_rows, cols, c.ldk, AT_BK) != M5_OK) return M5_ERR_CUDA;
   if (at_tmap(&tv, c.V, c.k_rows, cols, c.ldv, AT_BK) != M5_OK) return M5_ERR_CUDA;
-  if (at_tmap(&tkl, split ? c.Klo : c.K, c.k_rows, cols, c.ldk, AT_BK) != M5_OK) return M5_ERR_CUDA;
+  if (at_tmap(&tkl, kpair ? c.Klo : c.K, c.k_rows, cols, c.ldk, AT_BK) != M5_OK) return M5_ERR_CUDA;
   if (at_tmap(&tvl, split ? c.Vlo : c.V, c.k_rows, cols, c.ldv, AT_BK) != M5_OK) return M5_ERR_CUDA;
   static DeviceOnce once;
   unsigned long long bit;
   if (once.needed(bit)) {
-    if (cudaFuncSetAttribute(flash_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<false>::SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(flash_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<true>::SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(flash_tc5_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<false, false>::SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(flash_tc5_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<true, true>::SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(flash_tc5_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<true, false>::SMEM) != cudaSuccess)
       return M5_ERR_CUDA;
     once.done(bit);
   }
@@ -439,8 +444,9 @@ int flash_attn_tc5(const AttnCall& c, cudaStream_t stream) {
   p.Olo8 = c.Olo8; p.ldo8 = c.ldo8;
   p.scale_log2 = c.scale * 1.4426950408889634f;
   dim3 grid((c.max_q + AT_BQ - 1) / AT_BQ, c.n_heads, c.n_seqs);
-  if (split) flash_tc5_kernel<true><<<grid, AT_THREADS, AtCfg<true>::SMEM, stream>>>(tq, tk, tv, tkl, tvl, p);
-  else flash_tc5_kernel<false><<<grid, AT_THREADS, AtCfg<false>::SMEM, stream>>>(tq, tk, tv, tkl, tvl, p);
+  if (kpair) flash_tc5_kernel<true, true><<<grid, AT_THREADS, AtCfg<true, true>::SMEM, stream>>>(tq, tk, tv, tkl, tvl, p);
+  else if (split) flash_tc5_kernel<true, false><<<grid, AT_THREADS, AtCfg<true, false>::SMEM, stream>>>(tq, tk, tv, tkl, tvl, p);
+  else flash_tc5_kernel<false, false><<<grid, AT_THREADS, AtCfg<false, false>::SMEM, stream>>>(tq, tk, tv, tkl, tvl, p);
   return cudaGetLastError() == cudaSuccess ? M5_OK : M5_ERR_CUDA;
 }
 

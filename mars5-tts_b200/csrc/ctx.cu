@@ -226,7 +226,7 @@ int m5_dbg_attn_split(m5_ctx* ctx, const void* Q, const void* K, const void* V, 
                       int32_t ldq, int32_t ldk, int32_t ldv, void* O, void* Olo, int32_t ldo, int32_t n_heads,
                       int32_t n_seqs, int32_t max_q, const int32_t* q_start, const int32_t* q_len, const int32_t* k_start,
                       const int32_t* k_len, int32_t q_rows, int32_t k_rows) {
-  if (!ctx || !Klo || !Vlo || !Olo) return M5_ERR_ARG;
+  if (!ctx || !Vlo || !Olo) return M5_ERR_ARG;   // Klo == NULL: keys are single fp16 values (mixed8k)
   AttnCall c;
   c.Q = (const __half*)Q; c.K = (const __half*)K; c.V = (const __half*)V; c.Klo = (const __half*)Klo; c.Vlo = (const __half*)Vlo;
   c.ldq = ldq; c.ldk = ldk; c.ldv = ldv; c.O = (__half*)O; c.Olo = (__half*)Olo; c.ldo = ldo; c.n_heads = n_heads;

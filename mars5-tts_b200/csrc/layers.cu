@@ -137,7 +137,9 @@ static int attn_block(m5_ctx* ctx, float* x, const SeqSet& seqs, int D, int H, i
   // mixed: sequences long enough for the tcgen05 kernel keep Q (and P) single fp16 and carry K, V, O as pairs; shorter
   // ones (text encoder, tiny inputs) run the fully split mma.sync kernel
   // (below ~1k rows the probabilities' fp16 rounding is averaged over too few keys: uncond pass at S = 300 measured 7e-4)
-  const bool tc5_split = (mode == M5_NUM_MIXED || mode == M5_NUM_MIXED8) && seqs.max_len >= 1024;
+  const bool tc5_split = num_is_mixed(mode) && seqs.max_len >= 1024;
+  // mixed8k: the keys of the (long) decoder self-attention stay single fp16 -- one S pass; cross-attention (137 keys) keeps pairs
+  const bool k_single = mode == M5_NUM_MIXED8K && tc5_split && !cross;
   const bool q_pair = split && !tc5_split;   // does the attention kernel consume low halves of Q?
   // f8 (decided by the caller, decoder_layer): fp8 lo pass in the projections around the tcgen05 pair attention; for self-
   // attention the caller's LayerNorm wrote the lo halves to s.h8 (and NOT to the fp16 lo slots)
@@ -162,11 +164,11 @@ static int attn_block(m5_ctx* ctx, float* x, const SeqSet& seqs, int D, int H, i
     a.flops_hint = 256.0 * H * seqs.cross_pairs;
   } else {
     a.K = s.qkv16 + D; a.V = s.qkv16 + 2 * D; a.ldk = a.ldv = 3 * D;
-    if (split) { a.Klo = s.qkv16_lo + D; a.Vlo = s.qkv16_lo + 2 * D; }
+    if (split) { a.Klo = k_single ? nullptr : s.qkv16_lo + D; a.Vlo = s.qkv16_lo + 2 * D; }
     a.k_start = seqs.start; a.k_len = seqs.klen ? seqs.klen : seqs.len; a.k_rows = rows;
     a.flops_hint = 256.0 * H * seqs.self_pairs;
   }
-  if (tc5_split) a.flops_hint *= 2.0;   // S and PV each run two UMMA passes (hi and lo tiles)
+  if (tc5_split) a.flops_hint *= k_single ? 1.5 : 2.0;   // S and PV each run two UMMA passes (hi and lo tiles); S one with single keys
   a.O = s.att16; a.ldo = split ? 2 * D : D; a.Olo = split ? s.att16 + D : nullptr;
   if (f8) { a.Olo = nullptr; a.Olo8 = s.att8; a.ldo8 = D; }
   a.n_heads = H; a.n_seqs = seqs.n; a.max_q = seqs.max_len; a.q_start = seqs.start; a.q_len = seqs.len; a.q_rows = rows;
@@ -195,7 +197,7 @@ int decoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const __half* mem16
   const int rows = seqs.rows;
   const bool split = mode != M5_NUM_FAST;
   // mixed8 applies where the tcgen05 pair attention does (long sequences) and the shapes run on the CTA-pair GEMM
-  const bool f8 = mode == M5_NUM_MIXED8 && seqs.max_len >= 1024 && w.sa_in_w8 && w.sa_out_w8 && w.ca_out_w8 && w.wv8 && w.w28 &&
+  const bool f8 = num_has_f8(mode) && seqs.max_len >= 1024 && w.sa_in_w8 && w.sa_out_w8 && w.ca_out_w8 && w.wv8 && w.w28 &&
                   D % 128 == 0 && ff % 128 == 0 && gemm_f8lo_eligible(rows, D, ctx->num_sms);
   M5_TRY(ln_to_f16(ctx, x, rows, D, w.n1w, w.n1b, eps, split, s.h16, f8 ? s.h8 : nullptr));
   M5_TRY(attn_block(ctx, x, seqs, D, H, mode, s, w.sa_in_w, w.sa_in_b, w.sa_out_w, w.sa_out_b, nullptr, nullptr, nullptr, nullptr,

@@ -65,7 +65,12 @@ void block_scratch_carve(Arena& a, BlockScratch& s, int rows, int mem_rows, int 
 //   M5_NUM_MIXED8  like MIXED, but in the big decoder GEMMs the lo half of every activation pair is an e5m2 value (x 2^-2)
 //                  multiplied against an e4m3 copy of the weights (x 2^+2) by a kind::f8f6f4 UMMA pass into the same TMEM
 //                  accumulator: the correction term needs ~4 bits, the fp8 pass runs at twice the fp16 rate
-enum { M5_NUM_FAST = 0, M5_NUM_PRECISE = 1, M5_NUM_MIXED = 2, M5_NUM_MIXED8 = 3 };
+//   M5_NUM_MIXED8K like MIXED8, but the keys of the decoder SELF-attention are single fp16 values (values stay pairs): their
+//                  rounding is averaged over the ~2k keys of a decoder sequence (1.3e-5 rms on the logits in the CPU emulation,
+//                  tools/precision_budget_mixed8.py) and S = Q K^T needs one UMMA pass instead of two
+enum { M5_NUM_FAST = 0, M5_NUM_PRECISE = 1, M5_NUM_MIXED = 2, M5_NUM_MIXED8 = 3, M5_NUM_MIXED8K = 4 };
+inline bool num_is_mixed(int mode) { return mode == M5_NUM_MIXED || mode == M5_NUM_MIXED8 || mode == M5_NUM_MIXED8K; }
+inline bool num_has_f8(int mode) { return mode == M5_NUM_MIXED8 || mode == M5_NUM_MIXED8K; }
 
 // x (fp32 [rows, D]) is updated in place.
 int encoder_layer(m5_ctx* ctx, float* x, const SeqSet& seqs, const EncLayerW& w, int D, int H, int ff, float eps,

@@ -394,7 +394,7 @@ extern "C" {
 int m5_nar_forward(m5_ctx* ctx, int32_t B, const int32_t* c_text, const int32_t* c_text_len, const int32_t* c_codes,
                    const int32_t* c_codes_len, const int32_t* x, const int32_t* x_len, int32_t t, int32_t drop_cond,
                    int32_t precise, int32_t mem, float* logits_out) {
-  if (!ctx || B <= 0 || precise < 0 || precise > 3) return M5_ERR_ARG;
+  if (!ctx || B <= 0 || precise < 0 || precise > M5_NUM_MIXED8K) return M5_ERR_ARG;
   ctx->last_error.clear();
   cudaSetDevice(ctx->device);
   NarWeights w;
@@ -441,7 +441,8 @@ int m5_nar_infer(m5_ctx* ctx, int32_t B, const int32_t* c_text, const int32_t* c
                  int32_t mem, const int32_t* x_init, const float* noise, uint64_t seed, const int64_t* utt_ids,
                  int32_t* out_codes) {
   if (!ctx || !cfg || B <= 0) return M5_ERR_ARG;
-  if (cfg->precise < 0 || cfg->precise > 3) return ctx->fail(M5_ERR_ARG, "m5_nar_cfg.precise must be 0 (fast), 1 (precise), 2 (mixed) or 3 (mixed8)");
+  if (cfg->precise < 0 || cfg->precise > M5_NUM_MIXED8K)
+    return ctx->fail(M5_ERR_ARG, "m5_nar_cfg.precise must be 0 (fast), 1 (precise), 2 (mixed), 3 (mixed8) or 4 (mixed8k)");
   ctx->last_error.clear();
   cudaSetDevice(ctx->device);
   NarWeights w;

@@ -183,10 +183,11 @@ class Engine:
             self._sched_cache[T] = np.ascontiguousarray(weights.diffusion_schedule(T).numpy())
         return self._sched_cache[T]
 
-    def make_nar_cfg(self, icfg: InferenceConfig, T=200, precise=capi.NUM_MIXED8, jump_len=1, jump_n_sample=1, scaled_forward=False):
-        """precise: NAR numerics (capi.NUM_FAST / NUM_PRECISE / NUM_MIXED / NUM_MIXED8; True == NUM_PRECISE).  The default,
-        mixed8, is the cheapest setting whose logits stay within 1e-3 max-abs of the fp32 reference (5.4e-4 measured at full
-        dims); it is `mixed` wherever the fp8 pass does not apply (short sequences, small batches)."""
+    def make_nar_cfg(self, icfg: InferenceConfig, T=200, precise=capi.NUM_DEFAULT, jump_len=1, jump_n_sample=1, scaled_forward=False):
+        """precise: NAR numerics (capi.NUM_FAST / NUM_PRECISE / NUM_MIXED / NUM_MIXED8 / NUM_MIXED8K; True == NUM_PRECISE).  The
+        default (capi.NUM_DEFAULT) is a setting whose logits stay within 1e-3 max-abs of the fp32 reference at full dims
+        (tests/test_zzz_fullsize_gpu.py); the fp8 modes are `mixed` wherever the fp8 pass does not apply (short sequences,
+        small batches)."""
         c = capi.NarCfg()
         c.T, c.x0_temp, c.guidance_w = T, icfg.x_0_temp, icfg.nar_guidance_w
         c.q0_override_steps, c.deep_clone, c.precise = icfg.q0_override_steps, int(icfg.deep_clone), int(precise)
@@ -216,7 +217,7 @@ class Engine:
         offs = np.concatenate([[0], np.cumsum(xlen)])
         return [out[offs[b]:offs[b + 1]] for b in range(len(c_text))]
 
-    def nar_forward(self, c_text, c_codes, x, t, drop_cond=False, precise=capi.NUM_MIXED8):
+    def nar_forward(self, c_text, c_codes, x, t, drop_cond=False, precise=capi.NUM_DEFAULT):
         B = len(c_text)
         text, tlen = _cat_i32(c_text), _i32([len(v) for v in c_text])
         codes, clen = _cat_i32(c_codes, 8), _i32([len(v) for v in c_codes])

@@ -173,5 +173,5 @@ def test_nar_cfg_and_ar_cfg_carry_every_inference_field():
     a = Engine.make_ar_cfg(e, ic, 321, 99)
     assert abs(a.typical_p - 0.6) < 1e-7 and a.top_k == 50 and a.max_len == 321 and a.eos_id == 99
     n = Engine.make_nar_cfg(e, ic, T=10, jump_len=2, jump_n_sample=3)
-    assert (n.T, n.q0_override_steps, n.deep_clone, n.precise, n.jump_len, n.jump_n_sample, n.scaled_forward) == (10, 7, 0, capi.NUM_MIXED8, 2, 3, 0)
+    assert (n.T, n.q0_override_steps, n.deep_clone, n.precise, n.jump_len, n.jump_n_sample, n.scaled_forward) == (10, 7, 0, capi.NUM_DEFAULT, 2, 3, 0)
     assert abs(n.x0_temp - 0.5) < 1e-7 and abs(n.guidance_w - 2.0) < 1e-7

@@ -147,19 +147,33 @@ def test_flash_attention_split_kv(m5lib, bare_ctx):
         rc = m5lib.m5_dbg_attn_split(bare_ctx, ptr(Q), ptr(Kh), ptr(Vh), ptr(Kl), ptr(Vl), D, D, D, ptr(O), ptr(Ol), D, H, len(q_lens),
                                      max(q_lens), ptr(qs), ptr(ql), ptr(ks), ptr(kl), nq, nk)
         capi.check(bare_ctx, rc, "attn_split")
+        # mixed8k: keys single fp16 (Klo = NULL), values pairs
+        Ok, Okl = torch.zeros(nq, D, device=DEV, dtype=torch.float16), torch.zeros(nq, D, device=DEV, dtype=torch.float16)
+        rc = m5lib.m5_dbg_attn_split(bare_ctx, ptr(Q), ptr(Kh), ptr(Vh), None, ptr(Vl), D, D, D, ptr(Ok), ptr(Okl), D, H, len(q_lens),
+                                     max(q_lens), ptr(qs), ptr(ql), ptr(ks), ptr(kl), nq, nk)
+        capi.check(bare_ctx, rc, "attn_split (single keys)")
         Op = torch.zeros(nq, D, device=DEV, dtype=torch.float16)
         rc = m5lib.m5_dbg_attn(bare_ctx, ptr(Q), ptr(Kh), ptr(Vh), D, D, D, ptr(Op), D, H, len(q_lens), max(q_lens), ptr(qs), ptr(ql),
                                ptr(ks), ptr(kl), 0, 2, nq, nk)
         capi.check(bare_ctx, rc, "attn")
         _sync(m5lib, bare_ctx)
-        e_split = e_plain = 0.0
+        e_split = e_plain = e_ksingle = e_kh = 0.0
         for i, (qn, kn) in enumerate(zip(q_lens, k_lens)):
             q0, k0 = cs(q_lens)[i], cs(k_lens)[i]
-            ref = _attn_ref(Q[q0:q0 + qn].float().view(qn, H, 64), K32[k0:k0 + kn].view(kn, H, 64), V32[k0:k0 + kn].view(kn, H, 64)).reshape(qn, D)
+            qv = Q[q0:q0 + qn].float().view(qn, H, 64)
+            ref = _attn_ref(qv, K32[k0:k0 + kn].view(kn, H, 64), V32[k0:k0 + kn].view(kn, H, 64)).reshape(qn, D)
+            # what the single-key kernel computes exactly: fp16-rounded keys, unrounded values
+            ref_kh = _attn_ref(qv, Kh[k0:k0 + kn].float().view(kn, H, 64), V32[k0:k0 + kn].view(kn, H, 64)).reshape(qn, D)
             e_split = max(e_split, ((O[q0:q0 + qn].float() + Ol[q0:q0 + qn].float()) - ref).abs().max().item())
             e_plain = max(e_plain, (Op[q0:q0 + qn].float() - ref).abs().max().item())
-        print(f"split-KV attention: max-abs {e_split:.2e} (plain fp16 kernel {e_plain:.2e}), keys {k_lens}")
+            e_ksingle = max(e_ksingle, ((Ok[q0:q0 + qn].float() + Okl[q0:q0 + qn].float()) - ref).abs().max().item())
+            e_kh = max(e_kh, ((Ok[q0:q0 + qn].float() + Okl[q0:q0 + qn].float()) - ref_kh).abs().max().item())
+        print(f"split-KV attention: max-abs {e_split:.2e} (plain fp16 kernel {e_plain:.2e}; single keys + value pairs {e_ksingle:.2e}, "
+              f"{e_kh:.2e} against the softmax of the ROUNDED keys), keys {k_lens}")
         assert e_split < 1e-3 and e_split < 0.5 * e_plain, (k_lens, e_split, e_plain)
+        # single keys: the same kernel minus the K_lo pass -- against the softmax of the rounded keys it is as close as the pair
+        # kernel is against the unrounded one (kernel correctness); against the unrounded keys it sits between pair and plain
+        assert e_kh < 1e-3 and e_kh < 0.5 * e_plain and e_ksingle <= 1.05 * e_plain + 1e-6, (k_lens, e_kh, e_ksingle, e_plain)
 
 
 # ------------------------------------------------------------------------------------------------ full-size pipelines
@@ -195,10 +209,11 @@ def test_nar_forward_full_dims_absolute_tolerance(full_engine):
         ref = nar_oracle.nar_forward(nar_sd, cfg, text, codes, x, t, drop_cond=drop).numpy()
         scale = float(np.abs(ref).max())
         errs = {}
-        for name, mode in (("fast", cp.NUM_FAST), ("mixed", cp.NUM_MIXED), ("mixed8", cp.NUM_MIXED8), ("precise", cp.NUM_PRECISE)):
+        for name, mode in (("fast", cp.NUM_FAST), ("mixed", cp.NUM_MIXED), ("mixed8", cp.NUM_MIXED8), ("mixed8k", cp.NUM_MIXED8K),
+                           ("precise", cp.NUM_PRECISE)):
             # mixed8's fp8 pass lives in the CTA-pair GEMM, which needs >= 74 tile pairs: three copies of the utterance in one
             # packed batch (4950 decoder rows) make the shapes eligible; every copy must give the same logits
-            rep = 3 if mode == cp.NUM_MIXED8 else 1
+            rep = 3 if mode in (cp.NUM_MIXED8, cp.NUM_MIXED8K) else 1
             outs = eng.nar_forward([text.numpy()] * rep, [codes.numpy()] * rep, [x.numpy()] * rep, t, drop_cond=drop, precise=mode)
             got = outs[0]
             if rep > 1:
@@ -208,6 +223,7 @@ def test_nar_forward_full_dims_absolute_tolerance(full_engine):
               ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
         assert errs["mixed"] < 1e-3, errs
         assert errs["mixed8"] < 1e-3, errs
+        assert errs["mixed8k"] < 1e-3, errs
         assert errs["precise"] < 1e-3, errs
         assert errs["fast"] < 1e-3 * max(1.0, scale), errs
 
@@ -266,11 +282,13 @@ def test_nar_infer_full_dims_code_agreement(full_engine):
     codes = [torch.randint(0, 1024, (Pf, 8), generator=g).numpy().astype(np.int32) for _ in range(B)]
     l0 = [torch.randint(0, 1024, (N,), generator=g).numpy().astype(np.int32) for _ in range(B)]
     out = {}
-    for name, mode in (("precise", cp.NUM_PRECISE), ("mixed", cp.NUM_MIXED), ("mixed8", cp.NUM_MIXED8), ("fast", cp.NUM_FAST)):
+    for name, mode in (("precise", cp.NUM_PRECISE), ("mixed", cp.NUM_MIXED), ("mixed8", cp.NUM_MIXED8), ("mixed8k", cp.NUM_MIXED8K),
+                       ("fast", cp.NUM_FAST)):
         ncfg = eng.make_nar_cfg(InferenceConfig(), T=20, precise=mode)
         out[name] = np.stack(eng.nar_infer(texts, codes, l0, ncfg, seed=5, utt_ids=[100, 101]))
-    mm = {k: float((out[k] != out["precise"]).mean()) for k in ("mixed", "mixed8", "fast")}
-    print(f"NAR codes after T=20 at full dims vs precise: mixed {mm['mixed']:.4%} differ, mixed8 {mm['mixed8']:.4%}, fast {mm['fast']:.4%} differ")
+    mm = {k: float((out[k] != out["precise"]).mean()) for k in ("mixed", "mixed8", "mixed8k", "fast")}
+    print(f"NAR codes after T=20 at full dims vs precise: mixed {mm['mixed']:.4%} differ, mixed8 {mm['mixed8']:.4%}, "
+          f"mixed8k {mm['mixed8k']:.4%}, fast {mm['fast']:.4%} differ")
     assert mm["mixed"] <= 0.02, mm
     assert mm["mixed"] <= mm["fast"] + 1e-9 or mm["fast"] < 0.02, mm
 
