@@ -20,6 +20,7 @@ struct GemmEpi {
   const float* colscale;  // [N] fp32 or null (Vocos layer-scale gamma)
   void* out;              // fp32 or fp16, row stride ldc (elements)
   void* out_lo;           // split modes: low halves
+  int lo_from_col;        // E_F16_SPLIT: columns below it get no lo half (nobody reads it: e.g. the queries of the pair attention)
   int ldc;
   uint8_t* out_lo8;  // E_SWIGLU_SPLIT8: lo halves as e5m2
   int ldc8;
@@ -72,16 +73,17 @@ __device__ __forceinline__ void epi_store4(const GemmEpi& epi, float (&v)[4], co
     // fp16 (hi, lo) pair of every value: hi = rn(v), lo = rn(v - hi); the mixed / precise NAR modes
     __half* o = reinterpret_cast<__half*>(epi.out) + (size_t)row * epi.ldc + col;
     __half* ol = reinterpret_cast<__half*>(epi.out_lo) + (size_t)row * epi.ldc + col;
+    const bool want_lo = col >= epi.lo_from_col;   // uniform over the 4 columns (lo_from_col % 4 == 0)
     __half h[4], l[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) { h[e] = __float2half_rn(v[e]); l[e] = __float2half_rn(v[e] - __half2float(h[e])); }
     if (full4) {
       *reinterpret_cast<uint2*>(o) = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
-      *reinterpret_cast<uint2*>(ol) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+      if (want_lo) *reinterpret_cast<uint2*>(ol) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
     } else {
 #pragma unroll
       for (int e = 0; e < 3; ++e)
-        if (col + e < N) { o[e] = h[e]; ol[e] = l[e]; }
+        if (col + e < N) { o[e] = h[e]; if (want_lo) ol[e] = l[e]; }
     }
   } else if constexpr (KIND == E_SWIGLU_SPLIT) {
     __half* o = reinterpret_cast<__half*>(epi.out) + (size_t)row * epi.ldc + (col >> 1);

@@ -265,7 +265,7 @@ static int launch_kind(const GemmCall& g, cudaStream_t stream, int num_sms) {
   const int n_tiles = (g.N + BLOCK_N - 1) / BLOCK_N;
   const int grid = min(num_sms, m_tiles * n_tiles);
   GemmEpi e;
-  e.bias = g.bias; e.colscale = g.colscale; e.out = g.out; e.out_lo = g.out_lo; e.ldc = g.ldc;
+  e.bias = g.bias; e.colscale = g.colscale; e.out = g.out; e.out_lo = g.out_lo; e.lo_from_col = g.lo_from_col; e.ldc = g.ldc;
   e.out_lo8 = g.out_lo8; e.ldc8 = g.ldc8;
   e.mode = g.mode; e.act = g.act; e.accumulate = g.accumulate;
   gemm_tc5_kernel<BLOCK_N, KIND><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ta, tb, g.M, g.N, g.K, g.kwrap, g.awrap, e);

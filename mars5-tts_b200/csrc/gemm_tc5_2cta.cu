@@ -330,7 +330,7 @@ static int launch_2cta(const GemmCall& g, cudaStream_t stream, int num_sms) {
   const int n_tiles = (g.N + C2_BN - 1) / C2_BN;
   const int clusters = min(num_sms / 2, m_tiles * n_tiles);
   GemmEpi e;
-  e.bias = g.bias; e.colscale = g.colscale; e.out = g.out; e.out_lo = g.out_lo; e.ldc = g.ldc;
+  e.bias = g.bias; e.colscale = g.colscale; e.out = g.out; e.out_lo = g.out_lo; e.lo_from_col = g.lo_from_col; e.ldc = g.ldc;
   e.out_lo8 = g.out_lo8; e.ldc8 = g.ldc8;
   e.mode = g.mode; e.act = g.act; e.accumulate = g.accumulate;
   gemm_tc5_2cta_kernel<KIND><<<2 * clusters, C2_THREADS, C2_TOTAL, stream>>>(ta, tb, ta8, tb8, g.M, g.N, g.K, g.kwrap, g.awrap,

@@ -150,6 +150,8 @@ static int attn_block(m5_ctx* ctx, float* x, const SeqSet& seqs, int D, int H, i
   gq.out = s.qkv16; gq.ldc = qn;
   const bool q_out_pair = cross ? q_pair : split;   // the fused QKV projection always needs the K / V low halves
   gq.mode = q_out_pair ? M5_OUT_F16_SPLIT : M5_OUT_F16; gq.out_lo = q_out_pair ? s.qkv16_lo : nullptr;
+  // the tcgen05 pair attention reads no lo halves of the queries (columns < D), with single keys none below 2 D either
+  if (!cross && tc5_split) gq.lo_from_col = k_single ? 2 * D : D;
   if (f8 && !cross) use_f8(gq, D, s.h8, in_w8);
   M5_TRY(run_gemm(ctx, gq));
   AttnCall a;

@@ -38,6 +38,7 @@ struct GemmCall {
   const float* colscale = nullptr;
   void* out = nullptr;
   void* out_lo = nullptr;
+  int lo_from_col = 0;  // M5_OUT_F16_SPLIT: lo halves are written for columns >= lo_from_col only (a multiple of 4)
   int ldc = 0;
   int mode = M5_OUT_F32;
   int act = M5_ACT_NONE;
