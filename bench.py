@@ -398,9 +398,9 @@ def main():
     ap.add_argument("--ntok", type=int, default=0, help="profiling aid: override the target-text token count (N = 15 * ntok)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--also-fast", dest="also_fast", action="store_true", default=True,
-                    help="also time one step in fast mode and report it beside the headline (default: on, when the wall budget allows)")
-    ap.add_argument("--no-also-fast", dest="also_fast", action="store_false")
+    ap.add_argument("--also", default="fast", help="comma list of further NAR numerics modes: one step of each is timed and reported beside "
+                                                   "the headline (default: fast; skipped when the wall budget does not allow it)")
+    ap.add_argument("--no-also-fast", dest="also", action="store_const", const="")
     args = ap.parse_args()
     if args.precise >= 0:
         args.mode = "precise" if args.precise else "fast"
@@ -527,6 +527,10 @@ def main():
             torch.distributed.barrier()
         return allmax(e0.elapsed_time(e1)), wavs
 
+    also = [m for m in args.also.split(",") if m and m != args.mode]
+    for m in also:
+        if m not in MODES:
+            raise SystemExit(f"--also: unknown mode {m}")
     # ---- warm-up: W-1 short passes (full shapes, T = 8), then one complete step that calibrates the step time
     t_full_ms = None
     for i in range(args.warmup):
@@ -537,8 +541,7 @@ def main():
     n_steps = args.steps
     if t_full_ms is not None:
         reserve = (0 if (args.no_e2e or nar_only) else 1.08 * t_full_ms / 1e3) + (45 if (world == 1 and not args.no_cpu_baseline) else 0) + 15
-        if args.also_fast:
-            reserve += t_full_ms / 1e3
+        reserve += len(also) * t_full_ms / 1e3
         fit = int((BUDGET_S - allmax(elapsed()) - reserve) // (t_full_ms / 1e3))
         n_steps = max(1, min(args.steps, fit))
     sampler = ClockSampler(local)
@@ -561,9 +564,10 @@ def main():
     phases = {k: round(v / n_steps * 1e3, 1) for k, v in PHASE_S.items()}
     e2e_steps = 1  # one end-to-end step keeps the default run within minutes
     ms_e2e, wavs = (ms / n_steps, None) if (args.no_e2e or nar_only) else timed(e2e_steps, step_host)
-    fast_ms = None
-    if args.also_fast and mode != 0 and t_full_ms is not None and allmax(elapsed()) + 0.8 * t_full_ms / 1e3 + 60 < BUDGET_S:
-        fast_ms, _ = timed(1, lambda: step_dev(mode_=0))
+    other_ms = {}
+    for m in also:
+        if t_full_ms is not None and allmax(elapsed()) + 0.8 * t_full_ms / 1e3 + 60 < BUDGET_S:
+            other_ms[m], _ = timed(1, lambda: step_dev(mode_=MODES[m]))
     audio_total = wl["audio_s"] * world * n_steps
     value = audio_total / (ms / 1e3)
     if rank != 0:
@@ -609,9 +613,12 @@ def main():
            "dtype": "f16 operands (split hi/lo pairs where nar_numerics says so) / f32 accumulate", "data": "synthetic", "config": config,
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_ar": roofline_ar,
            "phase_ms_per_step": phases, "realtime_factor_per_gpu": value / world, "wall_s": round(elapsed(), 1)}
-    if fast_ms is not None:
-        out["fast_mode"] = {"value": wl["audio_s"] * world / (fast_ms / 1e3), "unit": UNIT, "steps": 1,
+    if "fast" in other_ms:
+        out["fast_mode"] = {"value": wl["audio_s"] * world / (other_ms["fast"] / 1e3), "unit": UNIT, "steps": 1,
                             "note": "nar_numerics=fast (fp16 operands everywhere): does NOT meet the 1e-3 max-abs logit bound"}
+    for m, v in other_ms.items():
+        if m != "fast":
+            out.setdefault("other_modes", {})[m] = {"value": wl["audio_s"] * world / (v / 1e3), "unit": UNIT, "steps": 1, "ms_per_step": v}
     if world == 1 and not args.no_cpu_baseline:
         wl1 = make_workload(size, 1, 1234, **wl_kw)
         v, detail, samp = cpu_port_sample(size, wl1, T, budget_s=25.0)
