@@ -13,7 +13,7 @@ OUT_F32, OUT_F16, OUT_SWIGLU_F16, OUT_F16_SPLIT, OUT_SWIGLU_F16_SPLIT = 0, 1, 2,
 ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
 NUM_FAST, NUM_PRECISE, NUM_MIXED, NUM_MIXED8, NUM_MIXED8K = 0, 1, 2, 3, 4   # m5_nar_cfg.precise (NAR numerics)
 NUM_NAMES = {"fast": NUM_FAST, "precise": NUM_PRECISE, "mixed": NUM_MIXED, "mixed8": NUM_MIXED8, "mixed8k": NUM_MIXED8K}
-NUM_DEFAULT = NUM_MIXED8   # what Mars5TTS and bench.py run: holds the 1e-3 max-abs logit bound at full dims
+NUM_DEFAULT = NUM_MIXED8K   # what Mars5TTS and bench.py run: holds the 1e-3 max-abs logit bound at full dims
 
 
 class ModelCfg(C.Structure):

@@ -277,7 +277,7 @@ def test_nar_infer_full_dims_code_agreement(full_engine):
     from mars5_tts_b200.engine import InferenceConfig
     size, _, _, eng, _ = full_engine
     g = torch.Generator().manual_seed(23)
-    B, Tc, Pf, N = 2, 60, 200, 400
+    B, Tc, Pf, N = 2, 60, 200, 1000   # S = 1200 rows: the tcgen05 pair attention (>= 1024) and the fp8 lo pass (>= 74 tile pairs) apply
     texts = [torch.randint(0, size["n_text"], (Tc,), generator=g).numpy().astype(np.int32) for _ in range(B)]
     codes = [torch.randint(0, 1024, (Pf, 8), generator=g).numpy().astype(np.int32) for _ in range(B)]
     l0 = [torch.randint(0, 1024, (N,), generator=g).numpy().astype(np.int32) for _ in range(B)]
@@ -289,7 +289,7 @@ def test_nar_infer_full_dims_code_agreement(full_engine):
     mm = {k: float((out[k] != out["precise"]).mean()) for k in ("mixed", "mixed8", "mixed8k", "fast")}
     print(f"NAR codes after T=20 at full dims vs precise: mixed {mm['mixed']:.4%} differ, mixed8 {mm['mixed8']:.4%}, "
           f"mixed8k {mm['mixed8k']:.4%}, fast {mm['fast']:.4%} differ")
-    assert mm["mixed"] <= 0.02, mm
+    assert mm["mixed"] <= 0.02 and mm["mixed8"] <= 0.02 and mm["mixed8k"] <= 0.02, mm
     assert mm["mixed"] <= mm["fast"] + 1e-9 or mm["fast"] < 0.02, mm
 
 

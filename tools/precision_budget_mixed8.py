@@ -1,7 +1,8 @@
 """CPU emulation of the `mixed8` NAR numerics on the full-size synthetic model: every big decoder GEMM as
 fp16 hi halves x fp16 weights + e5m2 lo halves (x 2^-2) x e4m3 weights (x 2^+2), queries and probabilities single fp16, everything
 else fp32.  Prints the max-abs / rms logit error against the fp32 forward (round 2: 4.4e-4 / 8.9e-5 at S = 800; the GPU measured
-5.3e-4 at S = 1650).   python tools/precision_budget_mixed8.py"""
+5.3e-4 at S = 1650).  M5_PB_KSINGLE=1 / M5_PB_VSINGLE=1 additionally round the decoder self-attention keys / values to single fp16
+(`mixed8k` = keys: 4.65e-4 / 8.90e-5, i.e. free; values too: 5.16e-4).   python tools/precision_budget_mixed8.py"""
 import os, sys, math, torch, torch.nn.functional as F
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import precision_budget as pb
@@ -26,6 +27,8 @@ def mha8(x_q, x_kv, w_in, b_in, w_out, b_out, H, cross):
         k = lin8(x_kv, w_in[D:2*D], b_in[D:2*D], f8=False); v = lin8(x_kv, w_in[2*D:], b_in[2*D:], f8=False)
     else:
         q = lin8(x_q, w_in[:D], b_in[:D]).half().float(); k = lin8(x_kv, w_in[D:2*D], b_in[D:2*D]); v = lin8(x_kv, w_in[2*D:], b_in[2*D:])
+        if os.environ.get("M5_PB_KSINGLE"): k = k.half().float()   # mixed8k: single-fp16 keys in the decoder self-attention
+        if os.environ.get("M5_PB_VSINGLE"): v = v.half().float()
     hd = D // H
     q,k,v = [t.view(-1,H,hd).transpose(0,1) for t in (q,k,v)]
     s = (q @ k.transpose(1,2)) / math.sqrt(hd)
