@@ -92,11 +92,11 @@ struct AttnTc5Params {
   float scale_log2;
 };
 
-// 32 score columns of this thread's row -> P (fp16, swizzled smem), partial row sums.
+// 32 score columns of this thread's row -> P (fp16, swizzled smem), partial row sums, running tile maximum.
 // FULL = no key of the chunk is beyond the sequence (every tile but possibly the last).
 template <bool FULL>
-M5_DEVINL void softmax_chunk(const uint32_t (&r)[32], int c, int kvalid, float scale, float m_used, float (&rs)[4], uint8_t* sp,
-                             int row) {
+M5_DEVINL void softmax_chunk(const uint32_t (&r)[32], int c, int kvalid, float scale, float m_used, float (&rs)[4],
+                             float (&tm)[2], uint8_t* sp, int row) {
   uint32_t pk[16];
 #pragma unroll
   for (int i = 0; i < 32; i += 2) {
@@ -105,10 +105,11 @@ M5_DEVINL void softmax_chunk(const uint32_t (&r)[32], int c, int kvalid, float s
     float p0 = ex2_approx(fmaf(s0, scale, -m_used));
     float p1 = ex2_approx(fmaf(s1, scale, -m_used));
     if (!FULL) {
-      if (c * 32 + i >= kvalid) p0 = 0.f;
-      if (c * 32 + i + 1 >= kvalid) p1 = 0.f;
+      if (c * 32 + i >= kvalid) { p0 = 0.f; s0 = -INFINITY; }
+      if (c * 32 + i + 1 >= kvalid) { p1 = 0.f; s1 = -INFINITY; }
     }
     rs[q & 3] += p0 + p1;
+    tm[q & 1] = fmax3(tm[q & 1], s0, s1);
     pk[q] = pack_half2(p0, p1);
   }
   // 32 columns = 4 chunks of 16 bytes of the 128-byte row; 16-byte chunk index XOR (row & 7) = 128B swizzle
@@ -269,30 +270,20 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     float m_used = -INFINITY, l_run = 0.f;
     uint32_t ra[32], rb[32];
     Ring sr, pr;   // score slot / P buffer of tile j
-    // the two barriers of tile j + 1 are looked at (non-blocking) while the exponentials of tile j run: a satisfied
-    // mbarrier wait still costs ~100 cycles of latency, twice per tile on the critical path of a softmax warp
-    bool s_pre = false, pv_pre = false;
     for (int j = 0; j < n_tiles; ++j) {
       const int kvalid = min(AT_BK, k_len - j * AT_BK);
       const bool full_tile = kvalid == AT_BK;             // warp-uniform: only the last tile needs key masking
       const uint32_t ts = tmem_base + sr.slot * AT_BK + lane_off;
       uint8_t* sp = smem + AT_OFF_P + pr.slot * AT_P_BYTES;
-      if (!s_pre) mbar_wait(bar + B_SREADY + sr.slot, sr.phase);
-      if (j >= 2 && !pv_pre) mbar_wait(bar + B_PVDONE + pr.slot, pr.phase ^ 1);   // PV_{j-2} no longer reads this P buffer
+      mbar_wait(bar + B_SREADY + sr.slot, sr.phase);
+      if (j >= 2) mbar_wait(bar + B_PVDONE + pr.slot, pr.phase ^ 1);   // PV_{j-2} no longer reads this P buffer
       tc5_fence_after();
       bool exact = (j == 0);
-      bool s_nxt = false, pv_nxt = false;
       float rs[4];
       for (;;) {
         tc5_ld_32x32(ts, ra);
         tc5_ld_32x32(ts + 32, rb);
         tc5_wait_ld();
-        if (j + 1 < n_tiles) {   // early look at tile j + 1: S_{j+1} computed?  PV_{j-1} done with the other P buffer?
-          Ring sn = sr, pn = pr;
-          sn.next(AT_SST); pn.next(2);
-          s_nxt = mbar_test(bar + B_SREADY + sn.slot, sn.phase);
-          pv_nxt = (j >= 1) && mbar_test(bar + B_PVDONE + pn.slot, pn.phase ^ 1);
-        }
         if (exact) {
           // exact path: row maximum first, then move the reference point (and O, l with it)
           float mx = full_tile ? chunk_max<true>(ra, 0, kvalid, -INFINITY) : chunk_max<false>(ra, 0, kvalid, -INFINITY);
@@ -323,25 +314,21 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           m_used = m_new;
         }
         rs[0] = rs[1] = rs[2] = rs[3] = 0.f;
+        float tm[2] = {-INFINITY, -INFINITY};
         if (full_tile) {
-          softmax_chunk<true>(ra, 0, kvalid, scale, m_used, rs, sp, row);
-          softmax_chunk<true>(rb, 1, kvalid, scale, m_used, rs, sp, row);
+          softmax_chunk<true>(ra, 0, kvalid, scale, m_used, rs, tm, sp, row);
+          softmax_chunk<true>(rb, 1, kvalid, scale, m_used, rs, tm, sp, row);
         } else {
-          softmax_chunk<false>(ra, 0, kvalid, scale, m_used, rs, sp, row);
-          softmax_chunk<false>(rb, 1, kvalid, scale, m_used, rs, sp, row);
+          softmax_chunk<false>(ra, 0, kvalid, scale, m_used, rs, tm, sp, row);
+          softmax_chunk<false>(rb, 1, kvalid, scale, m_used, rs, tm, sp, row);
         }
-        rs[0] = (rs[0] + rs[1]) + (rs[2] + rs[3]);
         if (exact) break;
-        // stale reference point: acceptable while no probability of this warp's rows exceeds 2^8 (fp16 range, and the point at
-        // which the reference is moved).  The row SUM of the tile bounds every term (all are >= 0, an overflowed one is +inf),
-        // so no running maximum has to be tracked: a tile whose sum exceeds 2^8 is redone on the exact path, which is always right
-        const bool grew = !(rs[0] <= 256.f);
+        // stale reference point: acceptable while no row of this warp outgrew it by more than 2^8
+        const bool grew = fmaf(fmaxf(tm[0], tm[1]), scale, -m_used) > 8.f;
         if (!__any_sync(0xffffffffu, grew)) break;
         exact = true;   // redo this tile on the exact path (S is still in TMEM, P has not been published)
       }
-      l_run += rs[0];
-      s_pre = __all_sync(0xffffffffu, s_nxt);
-      pv_pre = __all_sync(0xffffffffu, pv_nxt);
+      l_run += (rs[0] + rs[1]) + (rs[2] + rs[3]);
       fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc5_fence_before();
       __syncwarp();
