@@ -134,18 +134,48 @@ M5_DEVINL void stage_x(const ArDecodeParams& p, const ArGemm& g, int kbase, cons
       s_scale[tid] = rsqrtf(ss / (float)p.D + p.eps);
     }
     __syncthreads();
+    // warp w stages rows w, w + 8, ...; a lane covers the float4 columns lane, lane + 32, ... of the slice.  Every load of a
+    // pair of rows is requested before the first one is used: the slice arrives in ONE or two L2 round trips instead of one
+    // per float4 (a loop of dependent load -> convert -> store iterations cost 12 - 24 serial round trips per GEMM phase)
+    const int warp = tid >> 5, lane = tid & 31;
     const int quads = g.kslice / 4;
-    for (int i = tid; i < BT * quads; i += AD_THREADS) {
-      const int row = i / quads, c = (i - row * quads) * 4;
-      uint2 o = make_uint2(0u, 0u);
-      if (row < p.B) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(p.x + (size_t)row * p.D + kbase + c));
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + kbase + c));
-        const float sc = s_scale[row];
-        o.x = pack_half2((v.x * sc) * gm.x, (v.y * sc) * gm.y);
-        o.y = pack_half2((v.z * sc) * gm.z, (v.w * sc) * gm.w);
+    constexpr int MAXC = (AD_MAX_KSLICE / 4 + 31) / 32;   // float4 columns per lane
+    constexpr int RB = 2;                                  // rows in flight per warp
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 gm[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int q = lane + 32 * c;
+      gm[c] = q < quads ? __ldg(reinterpret_cast<const float4*>(gamma + kbase) + q) : z4;
+    }
+    for (int r0 = warp; r0 < BT; r0 += AD_WARPS * RB) {
+      float4 v[RB][MAXC];
+#pragma unroll
+      for (int rr = 0; rr < RB; ++rr) {
+        const int row = r0 + rr * AD_WARPS;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+          const int q = lane + 32 * c;
+          v[rr][c] = (row < p.B && q < quads) ? __ldcg(reinterpret_cast<const float4*>(p.x + (size_t)row * p.D + kbase) + q) : z4;
+        }
       }
-      *reinterpret_cast<uint2*>(xs + (size_t)row * xstride + c * 2) = o;
+#pragma unroll
+      for (int rr = 0; rr < RB; ++rr) {
+        const int row = r0 + rr * AD_WARPS;
+        if (row >= BT) continue;
+        const float sc = s_scale[row];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+          const int q = lane + 32 * c;
+          if (q >= quads) continue;
+          uint2 o = make_uint2(0u, 0u);
+          if (row < p.B) {
+            o.x = pack_half2((v[rr][c].x * sc) * gm[c].x, (v[rr][c].y * sc) * gm[c].y);
+            o.y = pack_half2((v[rr][c].z * sc) * gm[c].z, (v[rr][c].w * sc) * gm[c].w);
+          }
+          *reinterpret_cast<uint2*>(xs + (size_t)row * xstride + q * 8) = o;
+        }
+      }
     }
   } else {
     const int vec_per_row = g.kslice / 8;
@@ -224,41 +254,81 @@ M5_DEVINL void gemm_phase(const ArDecodeParams& p, const ArGemm& g, const float*
     const float* base = p.scratch + (size_t)(it.tile * g.ksplit) * (32 * AD_ROWS);
     const int nrow0 = it.tile * AD_ROWS;
     if constexpr (EPI == EPI_SWIGLU) {
-      for (int i = tid; i < BT * (AD_ROWS / 2); i += AD_THREADS) {
+      // a thread owns IT (batch row, column pair) outputs; the partial sums of ALL of them are requested before the first is
+      // used (AD_RED slices per round), then summed in slice order (deterministic)
+      constexpr int IT = BT * (AD_ROWS / 2) / AD_THREADS;
+      float a[IT], c[IT];
+      bool ok[IT];
+#pragma unroll
+      for (int u = 0; u < IT; ++u) {
+        const int i = tid + u * AD_THREADS;
         const int b = i / (AD_ROWS / 2), pr = i - b * (AD_ROWS / 2);
-        const int n = nrow0 + 2 * pr;
-        if (b >= p.B || n + 1 >= g.N) continue;
-        float a = 0.f, c = 0.f;
-        for (int s0 = 0; s0 < g.ksplit; s0 += AD_RED) {   // AD_RED slices' loads in flight, summed in slice order (deterministic)
-          float2 v2[AD_RED];
+        ok[u] = b < p.B && nrow0 + 2 * pr + 1 < g.N;
+        a[u] = c[u] = 0.f;
+      }
+      for (int s0 = 0; s0 < g.ksplit; s0 += AD_RED) {
+        float2 v2[IT][AD_RED];
+#pragma unroll
+        for (int u = 0; u < IT; ++u) {
+          const int i = tid + u * AD_THREADS;
+          const int b = i / (AD_ROWS / 2), pr = i - b * (AD_ROWS / 2);
 #pragma unroll
           for (int e = 0; e < AD_RED; ++e)
-            v2[e] = (s0 + e < g.ksplit) ? __ldcg(reinterpret_cast<const float2*>(base + (size_t)(s0 + e) * (32 * AD_ROWS) + (size_t)b * AD_ROWS + 2 * pr))
-                                        : make_float2(0.f, 0.f);
-#pragma unroll
-          for (int e = 0; e < AD_RED; ++e) { a += v2[e].x; c += v2[e].y; }
+            v2[u][e] = (ok[u] && s0 + e < g.ksplit)
+                           ? __ldcg(reinterpret_cast<const float2*>(base + (size_t)(s0 + e) * (32 * AD_ROWS) + (size_t)b * AD_ROWS + 2 * pr))
+                           : make_float2(0.f, 0.f);
         }
-        p.g16[(size_t)b * (g.N / 2) + (n >> 1)] = __float2half_rn((a / (1.f + __expf(-a))) * c);
+#pragma unroll
+        for (int u = 0; u < IT; ++u) {
+#pragma unroll
+          for (int e = 0; e < AD_RED; ++e) { a[u] += v2[u][e].x; c[u] += v2[u][e].y; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < IT; ++u) {
+        const int i = tid + u * AD_THREADS;
+        const int b = i / (AD_ROWS / 2), pr = i - b * (AD_ROWS / 2);
+        if (ok[u]) p.g16[(size_t)b * (g.N / 2) + ((nrow0 + 2 * pr) >> 1)] = __float2half_rn((a[u] / (1.f + __expf(-a[u]))) * c[u]);
       }
     } else {
-      // warp w owns batch rows w, w + 8, ...; a lane owns 4 consecutive weight rows (= output columns) of the tile
-      for (int b = warp; b < BT; b += AD_WARPS) {
-        if (b >= p.B) continue;
-        float4 r_pre = make_float4(0.f, 0.f, 0.f, 0.f);   // residual row segment, requested before the partial sums
+      // warp w owns batch rows w, w + 8, ...; a lane owns 4 consecutive weight rows (= output columns) of the tile.  The
+      // residual segments and the partial sums of ALL rows of the warp are requested together (AD_RED slices per round), the
+      // sums run in slice order (deterministic): ksplit / AD_RED L2 round trips per tile instead of one chain per batch row
+      constexpr int RW = BT / AD_WARPS;
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 acc[RW], rpre[RW];
+      const bool vec = nrow0 + 4 * lane + 3 < g.N && (ldo & 3) == 0;
+#pragma unroll
+      for (int u = 0; u < RW; ++u) {
+        const int b = warp + u * AD_WARPS;
+        acc[u] = z4; rpre[u] = z4;
         if constexpr (EPI == EPI_RESID) {
-          if (nrow0 + 4 * lane + 3 < g.N && (ldo & 3) == 0)
-            r_pre = __ldcg(reinterpret_cast<const float4*>(out_f32 + (size_t)b * ldo + nrow0 + 4 * lane));
+          if (b < p.B && vec) rpre[u] = __ldcg(reinterpret_cast<const float4*>(out_f32 + (size_t)b * ldo + nrow0 + 4 * lane));
         }
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s0 = 0; s0 < g.ksplit; s0 += AD_RED) {   // AD_RED slices' loads in flight, summed in slice order (deterministic)
-          float4 q[AD_RED];
+      }
+      for (int s0 = 0; s0 < g.ksplit; s0 += AD_RED) {
+        float4 q[RW][AD_RED];
+#pragma unroll
+        for (int u = 0; u < RW; ++u) {
+          const int b = warp + u * AD_WARPS;
 #pragma unroll
           for (int e = 0; e < AD_RED; ++e)
-            q[e] = (s0 + e < g.ksplit) ? __ldcg(reinterpret_cast<const float4*>(base + (size_t)(s0 + e) * (32 * AD_ROWS) + (size_t)b * AD_ROWS + 4 * lane))
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int e = 0; e < AD_RED; ++e) { v.x += q[e].x; v.y += q[e].y; v.z += q[e].z; v.w += q[e].w; }
+            q[u][e] = (b < p.B && s0 + e < g.ksplit)
+                          ? __ldcg(reinterpret_cast<const float4*>(base + (size_t)(s0 + e) * (32 * AD_ROWS) + (size_t)b * AD_ROWS + 4 * lane))
+                          : z4;
         }
+#pragma unroll
+        for (int u = 0; u < RW; ++u) {
+#pragma unroll
+          for (int e = 0; e < AD_RED; ++e) { acc[u].x += q[u][e].x; acc[u].y += q[u][e].y; acc[u].z += q[u][e].z; acc[u].w += q[u][e].w; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RW; ++u) {
+        const int b = warp + u * AD_WARPS;
+        if (b >= p.B) continue;
+        float4 v = acc[u];
+        const float4 r_pre = rpre[u];
         const int n = nrow0 + 4 * lane;
         float* o = out_f32 + (size_t)b * ldo + n;
         float sq = 0.f;
