@@ -175,3 +175,23 @@ def test_nar_cfg_and_ar_cfg_carry_every_inference_field():
     n = Engine.make_nar_cfg(e, ic, T=10, jump_len=2, jump_n_sample=3)
     assert (n.T, n.q0_override_steps, n.deep_clone, n.precise, n.jump_len, n.jump_n_sample, n.scaled_forward) == (10, 7, 0, capi.NUM_DEFAULT, 2, 3, 0)
     assert abs(n.x0_temp - 0.5) < 1e-7 and abs(n.guidance_w - 2.0) < 1e-7
+
+
+def test_numerics_modes_agree_between_header_capi_and_bench():
+    """m5_nar_cfg.precise: the names bench.py accepts, the constants of capi.py, the enum of csrc/layers.h and the comment of
+    include/mars5_b200.h list the same modes; the default is one of the modes that hold the absolute 1e-3 logit bound
+    (tests/test_zzz_fullsize_gpu.py asserts it for mixed, mixed8, mixed8k, precise)."""
+    import os
+    import re
+    import bench
+    from mars5_tts_b200 import capi
+    assert bench.MODES == capi.NUM_NAMES
+    assert sorted(capi.NUM_NAMES.values()) == list(range(len(capi.NUM_NAMES)))
+    assert capi.NUM_DEFAULT in (capi.NUM_MIXED, capi.NUM_MIXED8, capi.NUM_MIXED8K, capi.NUM_PRECISE)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    enum = re.search(r"enum \{ (M5_NUM_FAST[^}]*)\}", open(os.path.join(root, "mars5-tts_b200", "csrc", "layers.h")).read()).group(1)
+    vals = {k.strip()[len("M5_NUM_"):].lower(): int(v) for k, v in (kv.split("=") for kv in enum.split(","))}
+    assert vals == capi.NUM_NAMES
+    hdr = open(os.path.join(root, "include", "mars5_b200.h")).read()
+    for name, v in capi.NUM_NAMES.items():
+        assert re.search(rf"\b{v} {name}\b", hdr), (name, v)
