@@ -47,6 +47,32 @@ class InferenceConfig:
     ref_audio_pad: float = 0
 
 
+class _phase:
+    """NVTX range around one C-ABI call (tracing hook): the phase (AR generate, NAR reverse loop, vocoder, ...)
+    shows up by name in an ncu / nsys timeline.  A no-op when torch was built without NVTX."""
+    _ok = True
+
+    def __init__(self, name):
+        self.name, self.pushed = name, False
+
+    def __enter__(self):
+        if _phase._ok:
+            try:
+                torch.cuda.nvtx.range_push(self.name)
+                self.pushed = True
+            except Exception:
+                _phase._ok = False
+        return self
+
+    def __exit__(self, *exc):
+        if self.pushed:
+            try:
+                torch.cuda.nvtx.range_pop()
+            except Exception:
+                _phase._ok = False
+        return False
+
+
 def _i32(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
 
@@ -149,10 +175,11 @@ class Engine:
         nsteps = 0 if noise is None else noise.shape[1]
         dump = self._alloc(mem, (B, dump_steps, V), np.float32) if dump_steps else None
         self._fence(mem)
-        rc = self.lib.m5_ar_generate(self.ctx, B, capi.ptr(ids), capi.ptr(plen_a), capi.ptr(codes), capi.ptr(slen_a),
-                                     capi.ptr(nph_a), C.byref(ar_cfg), mem, capi.ptr(noise), nsteps, C.c_uint64(seed),
-                                     capi.ptr(utt_a), capi.ptr(out_ids), capi.ptr(out_len), capi.ptr(hit), capi.ptr(dump),
-                                     dump_steps)
+        with _phase("m5_ar_generate"):
+            rc = self.lib.m5_ar_generate(self.ctx, B, capi.ptr(ids), capi.ptr(plen_a), capi.ptr(codes), capi.ptr(slen_a),
+                                         capi.ptr(nph_a), C.byref(ar_cfg), mem, capi.ptr(noise), nsteps, C.c_uint64(seed),
+                                         capi.ptr(utt_a), capi.ptr(out_ids), capi.ptr(out_len), capi.ptr(hit), capi.ptr(dump),
+                                         dump_steps)
         capi.check(self.ctx, rc, "m5_ar_generate")
         return out_ids, out_len, hit, dump
 
@@ -171,8 +198,9 @@ class Engine:
         codes, slen = _cat_i32(spk_codes, 8), _i32([len(s) for s in spk_codes])
         V = self.dims["ar_vocab"]
         out = np.zeros((int(plen.sum()), V), dtype=np.float32)
-        rc = self.lib.m5_ar_forward(self.ctx, B, capi.ptr(ids), capi.ptr(plen), capi.ptr(codes), capi.ptr(slen),
-                                    capi.MEM_HOST, capi.ptr(out))
+        with _phase("m5_ar_forward"):
+            rc = self.lib.m5_ar_forward(self.ctx, B, capi.ptr(ids), capi.ptr(plen), capi.ptr(codes), capi.ptr(slen),
+                                        capi.MEM_HOST, capi.ptr(out))
         capi.check(self.ctx, rc, "m5_ar_forward")
         offs = np.concatenate([[0], np.cumsum(plen)])
         return [out[offs[b]:offs[b + 1]] for b in range(B)]
@@ -202,9 +230,10 @@ class Engine:
         utt_a = np.ascontiguousarray(np.asarray(utt, dtype=np.int64)) if utt is not None else None
         out = self._alloc(mem, (int(np.sum(xlen)), 8), np.int32)
         self._fence(mem)
-        rc = self.lib.m5_nar_infer(self.ctx, B, capi.ptr(text), capi.ptr(tlen_a), capi.ptr(codes), capi.ptr(clen_a),
-                                   capi.ptr(l0), capi.ptr(xlen_a), C.byref(nar_cfg), mem, capi.ptr(x_init), capi.ptr(noise),
-                                   C.c_uint64(seed), capi.ptr(utt_a), capi.ptr(out))
+        with _phase("m5_nar_infer"):
+            rc = self.lib.m5_nar_infer(self.ctx, B, capi.ptr(text), capi.ptr(tlen_a), capi.ptr(codes), capi.ptr(clen_a),
+                                       capi.ptr(l0), capi.ptr(xlen_a), C.byref(nar_cfg), mem, capi.ptr(x_init), capi.ptr(noise),
+                                       C.c_uint64(seed), capi.ptr(utt_a), capi.ptr(out))
         capi.check(self.ctx, rc, "m5_nar_infer")
         return out
 
@@ -224,9 +253,10 @@ class Engine:
         xs, xlen = _cat_i32(x, 8), _i32([len(v) for v in x])
         K = self.dims["n_classes"]
         out = np.zeros((int(xlen.sum()), 8, K), dtype=np.float32)
-        rc = self.lib.m5_nar_forward(self.ctx, B, capi.ptr(text), capi.ptr(tlen), capi.ptr(codes), capi.ptr(clen),
-                                     capi.ptr(xs), capi.ptr(xlen), int(t), int(drop_cond), int(precise), capi.MEM_HOST,
-                                     capi.ptr(out))
+        with _phase("m5_nar_forward"):
+            rc = self.lib.m5_nar_forward(self.ctx, B, capi.ptr(text), capi.ptr(tlen), capi.ptr(codes), capi.ptr(clen),
+                                         capi.ptr(xs), capi.ptr(xlen), int(t), int(drop_cond), int(precise), capi.MEM_HOST,
+                                         capi.ptr(out))
         capi.check(self.ctx, rc, "m5_nar_forward")
         offs = np.concatenate([[0], np.cumsum(xlen)])
         return [out[offs[b]:offs[b + 1]] for b in range(B)]
@@ -242,7 +272,8 @@ class Engine:
         flat = np.ascontiguousarray(np.concatenate(arrs))
         frames = [(int(n) + 319) // 320 for n in ns]
         out = np.zeros((int(np.sum(frames)), n_q), dtype=np.int32)
-        rc = self.lib.m5_encodec_encode(self.ctx, len(arrs), capi.ptr(flat), capi.ptr(ns), capi.MEM_HOST, int(n_q), capi.ptr(out))
+        with _phase("m5_encodec_encode"):
+            rc = self.lib.m5_encodec_encode(self.ctx, len(arrs), capi.ptr(flat), capi.ptr(ns), capi.MEM_HOST, int(n_q), capi.ptr(out))
         capi.check(self.ctx, rc, "m5_encodec_encode")
         offs = np.concatenate([[0], np.cumsum(frames)])
         return [out[offs[b]:offs[b + 1]] for b in range(len(arrs))]
@@ -252,7 +283,8 @@ class Engine:
         mem, nf_a = self._mem(codes), _i32(n_frames)
         out = self._alloc(mem, (int(np.sum(n_frames)) * self.dims["voc_hop"],), np.float32)
         self._fence(mem)
-        rc = self.lib.m5_vocode(self.ctx, len(n_frames), capi.ptr(codes), capi.ptr(nf_a), int(bandwidth_id), mem, capi.ptr(out))
+        with _phase("m5_vocode"):
+            rc = self.lib.m5_vocode(self.ctx, len(n_frames), capi.ptr(codes), capi.ptr(nf_a), int(bandwidth_id), mem, capi.ptr(out))
         capi.check(self.ctx, rc, "m5_vocode")
         return out
 
@@ -263,8 +295,9 @@ class Engine:
         cat, nf_a = _cat_i32(codes, 8), _i32(nf)
         out = np.zeros((int(np.sum(nf)) * self.dims["voc_hop"],), dtype=np.float32)
         st, en = np.zeros(len(nf), dtype=np.int64), np.zeros(len(nf), dtype=np.int64)
-        rc = self.lib.m5_vocode_trim(self.ctx, len(nf), capi.ptr(cat), capi.ptr(nf_a), int(bandwidth_id), capi.MEM_HOST, float(top_db),
-                                     int(frame_length), int(hop_length), capi.ptr(out), capi.ptr(st), capi.ptr(en))
+        with _phase("m5_vocode_trim"):
+            rc = self.lib.m5_vocode_trim(self.ctx, len(nf), capi.ptr(cat), capi.ptr(nf_a), int(bandwidth_id), capi.MEM_HOST, float(top_db),
+                                         int(frame_length), int(hop_length), capi.ptr(out), capi.ptr(st), capi.ptr(en))
         capi.check(self.ctx, rc, "m5_vocode_trim")
         offs = np.concatenate([[0], np.cumsum(nf)]) * self.dims["voc_hop"]
         return [out[offs[b]:offs[b + 1]] for b in range(len(codes))], [(int(a), int(b)) for a, b in zip(st, en)]

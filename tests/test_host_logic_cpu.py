@@ -1,4 +1,5 @@
 """CPU suite: host-side logic that needs no GPU (weight repack layout, schedule tables, tokenizer stand-ins, bench workload)."""
+import pytest
 import numpy as np
 import torch
 
@@ -195,3 +196,13 @@ def test_numerics_modes_agree_between_header_capi_and_bench():
     hdr = open(os.path.join(root, "include", "mars5_b200.h")).read()
     for name, v in capi.NUM_NAMES.items():
         assert re.search(rf"\b{v} {name}\b", hdr), (name, v)
+
+
+def test_phase_ranges_never_swallow_errors():
+    """engine._phase (NVTX range around every C-ABI call) pops its range on the way out and lets exceptions through."""
+    from mars5_tts_b200.engine import _phase
+    with _phase("m5_test") as r:
+        assert r.name == "m5_test"
+    with pytest.raises(ValueError):
+        with _phase("m5_test"):
+            raise ValueError("must propagate")
