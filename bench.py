@@ -6,7 +6,8 @@ One "step" = one pass of the hot path over one batch of B synthetic utterances (
 to N = 15 frames per text token = 1500 frames (random weights never emit EOS), T = 200 reverse steps with classifier-free
 guidance.  value  = audio seconds / second with inputs resident in HBM; e2e = the same through the host-buffer C ABI.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c5] [--mode fast|mixed|precise]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c5]
+                    [--mode fast|mixed|mixed8|mixed8k|precise] [--also MODE,MODE]
 
 N > 1: launched under torch.distributed.run, one rank per GPU; utterances shard by batch (weak scaling), weights are
 repacked on rank 0 and broadcast over NCCL, finished waveforms are all-gathered.  --impl reference times the reference's
