@@ -1,0 +1,175 @@
+"""CPU suite, build container only: the oracle (oracle/*.py, the checker of every GPU parity test) against the UNMODIFIED
+reference run LIVE (/root/reference/mars5/*) on freshly drawn inputs -- other seeds, other lengths and the edge cases (one text
+token, one reference frame, one decoder row, t = 0, no guidance, typical-p, tiny penalty windows) than the committed fixtures
+of tests/golden/ hold.  Skipped where the reference tree does not exist (the GPU box): nothing there may read /root/reference."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from mars5_tts_b200 import synth, weights
+from oracle import ar_oracle, nar_oracle
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "mars5")),
+                                reason="the unmodified reference tree exists only in the build container")
+torch.set_grad_enabled(False)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    sys.path.insert(0, REF)
+    try:
+        from mars5 import ar_generate as ref_ar
+        from mars5 import diffuser as ref_diff
+        from mars5 import samplers as ref_smp
+        from mars5.model import CodecLM, ResidualTransformer
+    finally:
+        sys.path.remove(REF)
+    size = synth.TINY
+    ar_sd, nar_sd = synth.make_ar_state(size), synth.make_nar_state(size)
+    V = size["n_text"] + size["n_speech"]
+    lm = CodecLM(n_vocab=V, dim=size["ar_dim"], nhead=size["ar_dim"] // 64, n_layers=size["ar_layers"],
+                 n_spk_layers=size["ar_spk_layers"], dim_ff_scale=7 / 3).eval()
+    nar = ResidualTransformer(n_text_vocab=size["n_text"] + 1, n_quant=1025, dim=size["nar_dim"], nhead=size["nar_dim"] // 64,
+                              enc_layers=size["nar_enc_layers"], dec_layers=size["nar_dec_layers"],
+                              n_spk_layers=size["nar_spk_layers"], t_emb_dim=size["nar_dim"], p_cond_drop=0, dropout=0).eval()
+    lm.load_state_dict(ar_sd, strict=True)
+    nar.load_state_dict(nar_sd, strict=True)
+    cfg = weights.dims_from_state(ar_sd, nar_sd, None, size["n_text"])
+    tt, st = synth.ByteTextTok(), synth.CodeSpeechTok()
+    n_text = len(tt.vocab)
+    return dict(ar=ref_ar, diff=ref_diff, smp=ref_smp, lm=lm, nar=nar, ar_sd=ar_sd, nar_sd=nar_sd, cfg=cfg, tt=tt, st=st,
+                n_text=n_text, V=n_text + len(st.vocab), eos=n_text + st.special_tokens["<|endofspeech|>"])
+
+
+# ------------------------------------------------------------------------------------------------ model evaluations
+@pytest.mark.parametrize("P,Pf,seed", [(1, 1, 0), (2, 3, 1), (17, 1, 2), (33, 26, 3)])
+def test_codeclm_forward_live(ref, P, Pf, seed):
+    g = torch.Generator().manual_seed(1000 + seed)
+    ids = torch.randint(0, ref["V"], (P,), generator=g)
+    spk = torch.randint(0, 1024, (Pf, 8), generator=g)
+    want = ref["lm"](ids[None], None, spk_reference=spk[None])[0]
+    got = ar_oracle.codeclm_forward(ref["ar_sd"], ref["cfg"], ids, spk)
+    assert got.shape == want.shape
+    assert (got - want).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("Tc,Pf,S,t,seed", [(1, 1, 1, 0, 0), (6, 2, 5, 3, 1), (13, 9, 23, 9, 2), (3, 17, 2, 199, 3)])
+@pytest.mark.parametrize("drop", [False, True])
+def test_residual_transformer_forward_live(ref, Tc, Pf, S, t, seed, drop):
+    g = torch.Generator().manual_seed(2000 + seed)
+    c_text = torch.randint(0, ref["n_text"], (Tc,), generator=g)
+    c_codes = torch.randint(0, 1024, (Pf, 8), generator=g)
+    x = torch.randint(0, 1025, (S, 8), generator=g)
+    want = ref["nar"](c_text[None], c_codes[None].clone(), torch.tensor([Tc]), torch.tensor([Pf]), x[None],
+                      torch.zeros(1, S, dtype=torch.bool), torch.tensor([t]), drop_cond=drop).permute(0, 1, 3, 2)[0]
+    got = nar_oracle.nar_forward(ref["nar_sd"], ref["cfg"], c_text, c_codes, x, t, drop)
+    assert got.shape == want.shape
+    assert (got - want).abs().max() < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------ AR loop
+AR_CASES = [
+    dict(temperature=0.7, top_k=200, top_p=0.2, typical_p=1.0, alpha_frequency=3, alpha_presence=0.4, penalty_window=80,
+         eos_penalty_decay=0.5, eos_penalty_factor=1),
+    dict(temperature=1.0, top_k=50, top_p=0.95, typical_p=1.0, alpha_frequency=1.5, alpha_presence=0.0, penalty_window=2,
+         eos_penalty_decay=0.8, eos_penalty_factor=2),
+    dict(temperature=1.3, top_k=1000, top_p=1.0, typical_p=0.6, alpha_frequency=0.0, alpha_presence=0.9, penalty_window=7,
+         eos_penalty_decay=0.5, eos_penalty_factor=0),
+]
+
+
+@pytest.mark.parametrize("case", range(len(AR_CASES)))
+@pytest.mark.parametrize("seed", [0, 1])
+def test_ar_generate_live_token_exact(ref, case, seed):
+    """ar_generate with torch.multinomial replaced by the exponential race on injected Exp(1) noise:
+    the oracle's token sequence must equal the reference's, EOS handling and max_len included."""
+    sc = AR_CASES[case]
+    g = torch.Generator().manual_seed(3000 + 10 * case + seed)
+    Pf, n_txt, n_sp = (5, 4, 2) if seed == 0 else (14, 11, 6)
+    spk = torch.randint(0, 1024, (Pf, 8), generator=g)
+    text_ids = [256] + torch.randint(0, 256, (n_txt,), generator=g).tolist() + [257]
+    prompt = torch.tensor(text_ids + (torch.randint(0, 1024, (n_sp,), generator=g) + ref["n_text"]).tolist())
+    steps = 10
+    max_len = len(prompt) + steps
+    noise = torch.empty(steps, ref["V"]).exponential_(1, generator=g)
+    n_ph = 3 + 4 * seed
+    calls = {"n": 0}
+    real = torch.multinomial
+
+    def fake_multinomial(p, num_samples, replacement=False):
+        q = p / noise[calls["n"]]
+        calls["n"] += 1
+        return q.argmax(dim=-1, keepdim=True)
+
+    torch.multinomial = fake_multinomial
+    try:
+        want = ref["ar"].ar_generate(ref["tt"], ref["st"], ref["lm"], prompt, spk, len(text_ids) + 1, max_len=max_len, fp16=False,
+                                     temperature=sc["temperature"], topk=sc["top_k"], top_p=sc["top_p"], typical_p=sc["typical_p"],
+                                     alpha_frequency=sc["alpha_frequency"], alpha_presence=sc["alpha_presence"],
+                                     penalty_window=sc["penalty_window"], eos_penalty_decay=sc["eos_penalty_decay"],
+                                     eos_penalty_factor=sc["eos_penalty_factor"], n_phones_gen=n_ph, vocode=False, use_kv_cache=True)
+    finally:
+        torch.multinomial = real
+    got, _ = ar_oracle.ar_generate(ref["ar_sd"], ref["cfg"], prompt, spk, sc, noise, max_len, n_ph, ref["eos"])
+    np.testing.assert_array_equal(got.numpy(), want.numpy())
+
+
+# ------------------------------------------------------------------------------------------------ NAR loop
+@pytest.mark.parametrize("deep,w,q0,T,seed", [(True, 3.0, 2, 5, 0), (False, 3.0, 0, 4, 1), (True, 1.0, 1, 3, 2), (False, 2.0, 20, 6, 3)])
+def test_perform_simple_inference_live_code_exact(ref, deep, w, q0, T, seed):
+    """perform_simple_inference with torch.randint / torch.rand_like replaced by injected draws: the oracle's codes equal the
+    reference's -- with and without classifier-free guidance (guidance_w = 1 skips the unconditional pass,
+    diffuser.py:361), q0 override steps beyond T, deep and shallow clone."""
+    g = torch.Generator().manual_seed(4000 + seed)
+    Pf, Tc, N = 3 + 4 * seed, 2 + 3 * seed, 1 + 3 * seed
+    c_text = torch.randint(0, ref["n_text"], (Tc,), generator=g)
+    c_codes = torch.randint(0, 1024, (Pf, 8), generator=g)
+    x_l0 = torch.randint(0, 1024, (N,), generator=g)
+    x_init = torch.randint(0, 1025, (N, 8), generator=g)
+    S_tot = N + (Pf if deep else 0)
+    u = torch.rand(T, 2, S_tot, 8, 1025, generator=g)
+    st_ = {"i": 0}
+    real_randint, real_rand_like = torch.randint, torch.rand_like
+
+    def fake_randint(lo, hi, shape, **kw):
+        return x_init[None].clone()
+
+    def fake_rand_like(t_, **kw):
+        step, draw = divmod(st_["i"], 2)
+        st_["i"] += 1
+        return u[step, draw][None].clone()
+
+    rd = ref["diff"]
+    torch.randint, torch.rand_like = fake_randint, fake_rand_like
+    try:
+        diff = rd.MultinomialDiffusion(1025, timesteps=T)
+        dsh = rd.DSH(last_greedy=True, x_0_temp=0.7, guidance_w=w, deep_clone=deep, jump_len=1, jump_n_sample=1,
+                     q0_override_steps=q0, enable_kevin_scaled_inference=True, progress=False)
+        _x = x_l0[None, :, None].repeat(1, 1, 8)
+        want = rd.perform_simple_inference(ref["nar"], (c_text[None], c_codes[None].clone(), torch.tensor([Tc]), torch.tensor([Pf]),
+                                                        _x, torch.zeros(1, N, dtype=torch.bool)),
+                                           diff, T, torch.float16, dsh=dsh, retain_quant0=True)[0]
+    finally:
+        torch.randint, torch.rand_like = real_randint, real_rand_like
+    assert st_["i"] == 2 * T - 1
+    ncfg = dict(T=T, deep_clone=deep, guidance_w=w, x0_temp=0.7, q0_override_steps=q0)
+    got = nar_oracle.nar_infer(ref["nar_sd"], ref["cfg"], c_text, c_codes, x_l0, ncfg, x_init, u)
+    np.testing.assert_array_equal(got.numpy(), want.numpy())
+
+
+# ------------------------------------------------------------------------------------------------ small pieces
+@pytest.mark.parametrize("T,jl,jn", [(200, 1, 1), (6, 2, 2), (10, 3, 2), (12, 5, 3), (7, 10, 10)])
+def test_get_schedule_live(ref, T, jl, jn):
+    assert nar_oracle.get_schedule(T, jl, jn) == list(ref["diff"].get_schedule(T, jump_len=jl, jump_n_sample=jn))
+
+
+@pytest.mark.parametrize("T", [3, 64, 128, 256])
+def test_diffusion_tables_live(ref, T):
+    d = ref["diff"].MultinomialDiffusion(1025, timesteps=T)
+    want = torch.stack([d.log_alpha, d.log_1_min_alpha, d.log_cumprod_alpha, d.log_1_min_cumprod_alpha]).numpy()
+    np.testing.assert_array_equal(torch.stack(nar_oracle.diffusion_tables(T)).numpy(), want)
+    np.testing.assert_array_equal(weights.diffusion_schedule(T).numpy(), want)
