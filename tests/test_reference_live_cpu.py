@@ -173,3 +173,62 @@ def test_diffusion_tables_live(ref, T):
     want = torch.stack([d.log_alpha, d.log_1_min_alpha, d.log_cumprod_alpha, d.log_1_min_cumprod_alpha]).numpy()
     np.testing.assert_array_equal(torch.stack(nar_oracle.diffusion_tables(T)).numpy(), want)
     np.testing.assert_array_equal(weights.diffusion_schedule(T).numpy(), want)
+
+
+# ------------------------------------------------------------------------------------------------ tokenisers
+@pytest.mark.parametrize("seed", [7, 8])
+def test_tokenisers_live(seed, tmp_path):
+    """Fresh minbpe-v1 models trained, saved and re-loaded by the reference's own classes on another seeded corpus; the native
+    merge engine behind mars5_tts_b200.bpe must encode / decode exactly like them (integer work)."""
+    import random
+    sys.path.insert(0, REF)
+    try:
+        from mars5.minbpe.codebook import CodebookTokenizer as RefCB
+        from mars5.minbpe.regex import GPT4_SPLIT_PATTERN, RegexTokenizer as RefRT
+    finally:
+        sys.path.remove(REF)
+    from mars5_tts_b200 import bpe
+    rng = random.Random(seed)
+    syl = ["ka", "to", "mi", "ra", "sen", "lo", "vi", "the", "ing", "qu", "é", "ü", "ñ", "漢", "字", "🙂", "'s", "12", "0"]
+    sep = [" ", " ", ", ", ". ", "! ", "?\n", "\n\n", "  ", "\t", " - ", "'ll ", ""]
+
+    def text(n):
+        return "".join("".join(rng.choice(syl) for _ in range(rng.randint(1, 4))) + rng.choice(sep) for _ in range(n))
+
+    # ---- text tokeniser
+    rt = RefRT()
+    rt.train(text(1500), 256 + 150)
+    rt.register_special_tokens({"<|startoftext|>": 406, "<|endoftext|>": 407})
+    rt.save(str(tmp_path / "text"))
+    ref_t, my_t = RefRT(), bpe.RegexTokenizer()
+    ref_t.load(str(tmp_path / "text.model"))
+    my_t.load(str(tmp_path / "text.model"))
+    assert len(my_t.vocab) == len(ref_t.vocab) and my_t.special_tokens == ref_t.special_tokens
+    samples = [text(rng.randint(1, 40)) for _ in range(25)] + ["", " ", "\n", "a", "<|startoftext|>hello<|endoftext|>", "   x   "]
+    for s in samples:
+        ids = ref_t.encode(s, allowed_special="all")
+        assert my_t.encode(s, allowed_special="all") == ids, repr(s[:40])
+        assert my_t.encode_ordinary(s) == ref_t.encode_ordinary(s)
+        assert my_t.decode(ids) == ref_t.decode(ids)
+    plain = [s for s in samples if "<|" not in s]
+    assert my_t.encode_batch(plain) == [ref_t.encode_ordinary(s) for s in plain]
+    # ---- speech tokeniser
+    hot = [rng.randrange(1024) for _ in range(30)]
+    codes = lambda n: [rng.choice(hot) if rng.random() < 0.8 else rng.randrange(1024) for _ in range(n)]
+    cb = RefCB(GPT4_SPLIT_PATTERN)
+    cb.train(" ".join(map(str, codes(6000))), 1024 + 200)
+    cb.register_special_tokens({"<|endofspeech|>": 1224})
+    cb.save(str(tmp_path / "speech"))
+    ref_s, my_s = RefCB(GPT4_SPLIT_PATTERN), bpe.CodebookTokenizer(bpe.GPT4_SPLIT_PATTERN)
+    ref_s.load(str(tmp_path / "speech.model"))
+    my_s.load(str(tmp_path / "speech.model"))
+    seqs = [codes(n) for n in (1, 2, 5, 31, 450, 1499)] + [[hot[0]] * 11 + [hot[1]] * 6]
+    for c in seqs:
+        txt = " ".join(map(str, c))
+        ids = ref_s.encode(txt)
+        assert my_s.encode(txt) == ids
+        assert my_s.decode_int(ids) == ref_s.decode_int(ids)
+        assert my_s.decode(ids) == ref_s.decode(ids)
+        mixed = ids[: len(ids) // 2] + [1224] + ids[len(ids) // 2:]
+        assert my_s.decode_int(mixed) == ref_s.decode_int(mixed)
+    assert my_s.encode_codes_batch(seqs) == [ref_s.encode(" ".join(map(str, c))) for c in seqs]
