@@ -2,10 +2,12 @@
 // path, `self.codec.encode(ref_audio[None])` at inference.py:233 with EncodecModel.encodec_model_24khz() at 6 kbps
 // (inference.py:87-88) -> (8, T) codes per reference clip, T = ceil(samples / 320).
 //
-// Third-party algorithm (package `encodec`, not in /root/reference): SEANetEncoder (reflect-padded non-causal convolutions
-// 1 -> 32 -> 64 -> 128 -> 256 -> 512 channels with strides 2, 4, 5, 8, one residual block per scale, ELU), a 2-layer LSTM
-// with skip connection, a 512 -> 128 convolution, then 8 greedy nearest-neighbour stages over 1024 x 128 codebooks.
-// oracle/encodec_oracle.py restates it with file citations; parity with the real package is UNPINNED.
+// Third-party algorithm (package `encodec`, not in /root/reference): SEANetEncoder (reflect-padded CAUSAL convolutions --
+// encodec_model_24khz is the causal model: the whole padding sits on the left -- 1 -> 32 -> 64 -> 128 -> 256 -> 512 channels
+// with strides 2, 4, 5, 8, one residual block per scale, ELU), a 2-layer LSTM with skip connection, a 512 -> 128 convolution,
+// then 8 greedy nearest-neighbour stages over 1024 x 128 codebooks.  oracle/encodec_oracle.py restates it with file citations
+// and is pinned against the independent `transformers` implementation of the same model (tests/test_encodec_hf_cpu.py);
+// parity with the released WEIGHTS needs the real package.
 //
 // A batch of B clips is processed together; activations are channel-major [C][sum_b L_b] with the clips side by side on the
 // time axis (each clip keeps its own reflect padding).  All arithmetic is fp32 on the CUDA cores: the output is an arg-max
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(EC_TT) enc_conv_kernel(const float* x, const i
   const int Lin = in_len[b], Lout = out_len[b];
   if (t0 >= Lout) return;
   const int total = k - stride;                       // padding_total (dilation 1 everywhere in the encoder)
-  const int right = total / 2, left = total - right;
+  const int right = 0, left = total;                  // causal SConv1d (encodec_model_24khz): all of it on the left
   const int extra = (Lout - 1) * stride + (k - total) - Lin;   // get_extra_padding_for_conv1d
   const int max_pad = max(left, right + extra);
   const int ext = Lin <= max_pad ? max_pad - Lin + 1 : 0;

@@ -2,12 +2,17 @@
 Mars5TTS runs on the reference clip before the loops (/root/reference/inference.py:87-88, 233:
 ``self.codec.encode(ref_audio[None])`` with ``EncodecModel.encodec_model_24khz()`` at 6 kbps -> (1, 8, T) codes).
 
-PARITY UNPINNED: the algorithm lives in the third-party package ``encodec`` (requirements.txt, unpinned; 0.1.1 at the
-time of the reference) whose source and weights are absent from /root/reference and from this image.  This file restates
-the published encodec 0.1.1 algorithm as recalled:
-  * encodec/modules/conv.py   SConv1d: non-causal, ``pad_mode='reflect'``, total padding = effective_kernel - stride split
-                              (left = total - total // 2, right = total // 2) plus the extra right padding that makes the
-                              last window full; pad1d's zero-extension for inputs not longer than the reflect pad
+PARITY PINNED AGAINST AN INDEPENDENT IMPLEMENTATION, UNPINNED AGAINST THE RELEASED WEIGHTS: the algorithm lives in the
+third-party package ``encodec`` (requirements.txt, unpinned; 0.1.1 at the time of the reference) whose source and weights are
+absent from /root/reference and from this image.  ``transformers`` (installed) ships an independent port of the same model
+(EncodecModel; EncodecConfig's defaults are facebook/encodec_24khz): tests/test_encodec_hf_cpu.py loads the synthetic state dict
+into it and requires identical codes and embeddings to 1e-6 on clips of 1 ... 4801 samples -- which is how the CAUSAL padding of
+the 24 kHz model was found (round 2; the first restatement used the 48 kHz model's split padding).  This file restates
+the published encodec 0.1.1 algorithm:
+  * encodec/modules/conv.py   SConv1d with ``causal=True`` (EncodecModel.encodec_model_24khz -> _get_model(..., causal=True)),
+                              ``pad_mode='reflect'``: total padding = effective_kernel - stride, ALL of it on the left, plus the
+                              extra right padding that makes the last window full; pad1d's zero-extension for inputs not longer
+                              than the reflect pad
   * encodec/modules/seanet.py SEANetEncoder(channels=1, dimension=128, n_filters=32, n_residual_layers=1, ratios=[8,5,4,2]
                               (applied reversed: 2,4,5,8), ELU(alpha=1), kernel_size=7, residual_kernel_size=3,
                               last_kernel_size=7, dilation_base=2, compress=2, true_skip=False, lstm=2)
@@ -45,20 +50,26 @@ def _pad1d_reflect(x, left, right):
     return padded[..., : padded.shape[-1] - extra]
 
 
-def sconv1d(x, w, b, stride=1, dilation=1):
-    """x (1, C_in, L) -> (1, C_out, ceil(L / stride))."""
+def _sconv1d(x, w, b, stride=1, dilation=1, causal=True):
+    """x (1, C_in, L) -> (1, C_out, ceil(L / stride)).  encodec_model_24khz is the CAUSAL model (`causal=True` in
+    EncodecModel._get_model): the whole padding_total goes to the left, only the extra padding that completes the last window to
+    the right.  (causal=False = the split padding of the 48 kHz model, kept for the cross-check against the HF implementation.)"""
     k = (w.shape[-1] - 1) * dilation + 1
     total = k - stride
     extra = _extra_padding(x.shape[-1], k, stride, total)
-    right = total // 2
-    left = total - right
+    if causal:
+        left, right = total, 0
+    else:
+        right = total // 2
+        left = total - right
     return F.conv1d(_pad1d_reflect(x, left, right + extra), w, b, stride=stride, dilation=dilation)
 
 
-def encoder_forward(sd, wav):
+def encoder_forward(sd, wav, causal=True):
     """wav (L,) float -> embeddings (128, T), T = ceil(L / 320)."""
     p = "encoder.model."
     x = wav[None, None].float()
+    sconv1d = lambda *a, **k: _sconv1d(*a, causal=causal, **k)
     x = sconv1d(x, sd[p + "0.conv.conv.weight"], sd[p + "0.conv.conv.bias"])
     idx = 1
     for ratio in RATIOS:
@@ -103,6 +114,9 @@ def rvq_encode(sd, emb, n_q=8):
     return torch.stack(codes, dim=1)
 
 
-def encode(sd, wav, n_q=8):
+def encode(sd, wav, n_q=8, causal=True):
     """EncodecModel.encode on one mono clip (no normalisation, no segmenting: encodec_model_24khz defaults)."""
-    return rvq_encode(sd, encoder_forward(sd, wav), n_q)
+    return rvq_encode(sd, encoder_forward(sd, wav, causal), n_q)
+
+
+sconv1d = _sconv1d

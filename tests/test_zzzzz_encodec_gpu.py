@@ -1,6 +1,8 @@
 """Encodec 24 kHz encoder + RVQ on the device (csrc/encodec.cu) against oracle/encodec_oracle.py
-on seeded synthetic weights at the released model's shapes.  The oracle restates the published encodec algorithm and is
-UNPINNED (the package is not installable here; tests/golden/make_encodec_golden.py pins it where it is).  Codes are an
+on seeded synthetic weights at the released model's shapes.  The oracle restates the published encodec algorithm (causal
+24 kHz model) and is pinned against the independent `transformers` implementation (tests/test_encodec_hf_cpu.py); the released
+weights stay unpinned (the package is not installable here; tests/golden/make_encodec_golden.py pins them where it is).  This
+file sorts last on purpose: the hot-path suites run before the widened rows.  Codes are an
 arg-max over distances computed in a different fp32 summation order than torch's, so a small mismatch rate on random
 codebooks is tolerated and the continuous embeddings are compared through the first-stage distances instead."""
 import numpy as np
