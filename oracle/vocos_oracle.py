@@ -6,7 +6,8 @@ in the reference's notebook log) whose source and weights (``charactr/vocos-enco
 /root/reference and from this image.  This file restates the published vocos 0.1.0 algorithm
 (vocos/pretrained.py codes_to_features + decode, vocos/models.py VocosBackbone, vocos/modules.py ConvNeXtBlock +
 AdaLayerNorm, vocos/heads.py ISTFTHead, vocos/spectral_ops.py ISTFT with "same" padding) as summarised in SURVEY.md
-Appendix C; it is self-consistent (torch.fft.irfft + F.fold) but could not be checked against the real package.
+Appendix C; it could not be checked against the real package.  Its iSTFT head is pinned against torch.istft on the span the
+"same" and "center" paddings share (tests/test_vocos_istft_cpu.py).
 State-dict keys follow vocos' module names so that a real checkpoint could be dropped in.
 """
 import torch
