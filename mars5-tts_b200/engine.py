@@ -366,6 +366,13 @@ class Mars5TTS:
         wav = self.engine.vocode([tokens.detach().cpu().numpy()], bandwidth_id=1)[0]
         return torch.from_numpy(wav)[None]
 
+    def get_speaker_embedding(self, ref_audio: torch.Tensor) -> torch.Tensor:
+        """The reference's analysis helper (inference.py:174-199: position 0 of the AR speaker encoder's output for a clip) is NOT
+        part of the hot path and has no entry point in the C ABI: the library computes that vector inside m5_ar_generate and never
+        exposes it.  Raising beats returning something different from the reference."""
+        raise NotImplementedError("Mars5TTS.get_speaker_embedding is outside the accelerated path (SURVEY.md section 8): compute it "
+                                  "with the reference's CodecLM (inference.py:174-199); tts() / tts_batch() / vocode() do not need it")
+
     def _prepare(self, text, ref_audio, ref_transcript, cfg):
         """Host glue of inference.py:212-258: tokenise, encode the reference clip, build the AR prompt."""
         if cfg.deep_clone and ref_transcript is None:
