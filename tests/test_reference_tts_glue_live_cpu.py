@@ -187,12 +187,15 @@ def _run_reference(ref_inf, r, text, ref_audio, transcript, cfg):
 
 
 @pytest.mark.parametrize("deep", [True, False])
-@pytest.mark.parametrize("text,transcript,n_ref", [("the quick brown rat", "we actually haven't managed", 2300), ("so on é", "to meet demand", 961)])
-def test_tts_glue_equals_live_reference(world, deep, text, transcript, n_ref):
+@pytest.mark.parametrize("text,transcript,n_ref,channels,pad", [("the quick brown rat", "we actually haven't managed", 2300, 0, 0.0),
+                                                                ("so on é", "to meet demand", 961, 0, 0.0),
+                                                                ("  we meet  ", "the rat", 1500, 2, 0.03)])   # stereo clip, left zero-pad (B.4-17)
+def test_tts_glue_equals_live_reference(world, deep, text, transcript, n_ref, channels, pad):
     ref_inf, r, o, size = world
-    ref_audio = torch.randn(n_ref, generator=torch.Generator().manual_seed(n_ref)) * 0.1
-    probe = o._prepare(text, ref_audio, transcript, InferenceConfig(deep_clone=deep, ref_audio_pad=0))
-    kw = dict(deep_clone=deep, ref_audio_pad=0, generate_max_len_override=len(probe["prompt"]) + AR_STEPS, temperature=1.0, top_k=60,
+    shape = (channels, n_ref) if channels else (n_ref,)
+    ref_audio = torch.randn(*shape, generator=torch.Generator().manual_seed(n_ref)) * 0.1
+    probe = o._prepare(text, ref_audio, transcript, InferenceConfig(deep_clone=deep, ref_audio_pad=pad))
+    kw = dict(deep_clone=deep, ref_audio_pad=pad, generate_max_len_override=len(probe["prompt"]) + AR_STEPS, temperature=1.0, top_k=60,
               top_p=0.9, rep_penalty_window=5, q0_override_steps=2)
     want_codes, want_wav = _run_reference(ref_inf, r, text, ref_audio, transcript, ref_inf.InferenceConfig(**kw))
     got_codes, got_wav = o.tts_batch([text], [ref_audio], [transcript], InferenceConfig(**kw))[0]
