@@ -57,6 +57,22 @@ def test_codeclm_forward_live(ref, P, Pf, seed):
     assert (got - want).abs().max() < 2e-5
 
 
+@pytest.mark.parametrize("pad_at", [0, 4, 11])
+def test_codeclm_forward_live_speaker_padding_quirk(ref, pad_at):
+    """the AR speaker encoder masks every reference frame from the first one whose codebook-0 entry is the pad
+    class 1024 (construct_padding_mask = cumsum of the equality), whatever comes after it."""
+    g = torch.Generator().manual_seed(1500 + pad_at)
+    ids = torch.randint(0, ref["V"], (9,), generator=g)
+    spk = torch.randint(0, 1024, (12, 8), generator=g)
+    spk[pad_at, 0] = 1024
+    want = ref["lm"](ids[None], None, spk_reference=spk[None])[0]
+    got = ar_oracle.codeclm_forward(ref["ar_sd"], ref["cfg"], ids, spk)
+    assert (got - want).abs().max() < 2e-5
+    spk2 = spk.clone()
+    spk2[pad_at + 1:] = torch.randint(0, 1024, spk2[pad_at + 1:].shape, generator=g)   # frames behind the pad do not matter
+    assert (ar_oracle.codeclm_forward(ref["ar_sd"], ref["cfg"], ids, spk2) - got).abs().max() == 0 or pad_at == 11
+
+
 @pytest.mark.parametrize("Tc,Pf,S,t,seed", [(1, 1, 1, 0, 0), (6, 2, 5, 3, 1), (13, 9, 23, 9, 2), (3, 17, 2, 199, 3)])
 @pytest.mark.parametrize("drop", [False, True])
 def test_residual_transformer_forward_live(ref, Tc, Pf, S, t, seed, drop):
