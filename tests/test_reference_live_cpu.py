@@ -248,3 +248,47 @@ def test_tokenisers_live(seed, tmp_path):
         mixed = ids[: len(ids) // 2] + [1224] + ids[len(ids) // 2:]
         assert my_s.decode_int(mixed) == ref_s.decode_int(mixed)
     assert my_s.encode_codes_batch(seqs) == [ref_s.encode(" ".join(map(str, c))) for c in seqs]
+
+
+# ------------------------------------------------------------------------------------------------ silence trim
+def test_trim_bounds_live():
+    """m5_trim_bounds (csrc/trim.cu host code, behind mars5_tts_b200.trim) against the reference's trim() on freshly drawn
+    waveforms: bursts at random places and levels, several top_db values, the shortest legal clip.  mars5/trim.py itself does not
+    run under numpy 2 (np.array(x, copy=False), trim.py:546): as in tests/golden/make_trim_golden.py the untouched module is handed
+    a numpy proxy with the numpy-1 meaning of that one call."""
+    sys.path.insert(0, REF)
+    try:
+        import mars5.trim as ref_trim
+    finally:
+        sys.path.remove(REF)
+    from mars5_tts_b200.trim import trim_bounds_batch
+
+    class Numpy1:
+        def __getattr__(self, name):
+            return getattr(np, name)
+
+        @staticmethod
+        def array(x, copy=True, subok=False, **kw):
+            return np.asarray(x) if copy is False else np.array(x, copy=copy, subok=subok, **kw)
+
+    real_np, ref_trim.np = ref_trim.np, Numpy1()
+    try:
+        g = torch.Generator().manual_seed(77)
+        wavs, want = [], []
+        for i in range(24):
+            n = int(torch.randint(1025, 60000, (1,), generator=g)) if i else 1025
+            y = torch.randn(n, generator=g) * (10.0 ** float(-torch.rand(1, generator=g) * 5))          # noise floor 1 .. 1e-5
+            for _ in range(int(torch.randint(0, 4, (1,), generator=g))):
+                a = int(torch.randint(0, n, (1,), generator=g))
+                b = min(n, a + int(torch.randint(1, 20000, (1,), generator=g)))
+                y[a:b] += torch.randn(b - a, generator=g) * float(torch.rand(1, generator=g))
+            top_db = [27, 60, 10, 40][i % 4]
+            _, idx = ref_trim.trim(y, top_db=top_db)
+            wavs.append((y.numpy(), top_db))
+            want.append((int(idx[0]), int(idx[1])))
+    finally:
+        ref_trim.np = real_np
+    for top_db in (27, 60, 10, 40):
+        sel = [i for i, (_, d) in enumerate(wavs) if d == top_db]
+        got = trim_bounds_batch([wavs[i][0] for i in sel], top_db=top_db)
+        assert got == [want[i] for i in sel], top_db
