@@ -198,14 +198,46 @@ def repack(ar_sd, nar_sd, voc_sd, dims, max_pos=4096, n_t=1000):
     return {k: v.contiguous() for k, v in t.items()}, alphas
 
 
+def encodec_keys_from_hf(sd):
+    """State dict of `transformers`' EncodecModel (facebook/encodec_24khz: `encoder.layers.{i}...`, `quantizer.layers.{q}.codebook.embed`)
+    -> the key names of the `encodec` package (`encoder.model.{i}...conv.conv...`, `quantizer.vq.layers.{q}._codebook.embed`) that
+    repack_encodec and oracle/encodec_oracle.py use.  Tensors are shared, decoder / bookkeeping entries dropped; a dict that already
+    has encodec's names is returned unchanged."""
+    import re
+    if not any(k.startswith("encoder.layers.") for k in sd):
+        return sd
+    out = {}
+    for k, v in sd.items():
+        m = re.match(r"encoder\.layers\.(\d+)\.(block\.\d+\.|shortcut\.)?conv\.(.+)$", k)
+        if m:
+            out[f"encoder.model.{m.group(1)}.{m.group(2) or ''}conv.conv.{m.group(3)}"] = v
+            continue
+        m = re.match(r"encoder\.layers\.(\d+)\.lstm\.(.+)$", k)
+        if m:
+            out[f"encoder.model.{m.group(1)}.lstm.{m.group(2)}"] = v
+            continue
+        m = re.match(r"quantizer\.layers\.(\d+)\.codebook\.embed$", k)
+        if m:
+            out[f"quantizer.vq.layers.{m.group(1)}._codebook.embed"] = v
+    return out
+
+
 def repack_encodec(enc_sd, n_q=8):
-    """Encodec 24 kHz encoder + RVQ state dict (EncodecModel.state_dict(), with or without weight norm folded) -> the "enc.*"
-    fp32 tensors csrc/encodec.cu consumes.  Key names: oracle/encodec_oracle.py header."""
+    """Encodec 24 kHz encoder + RVQ state dict -> the "enc.*" fp32 tensors csrc/encodec.cu consumes.  Accepts
+    EncodecModel.state_dict() of the `encodec` package (key names: oracle/encodec_oracle.py header) or of `transformers`'
+    EncodecModel, with the weight norm folded (`.weight`), in torch's old form (`.weight_g` / `.weight_v`) or as a
+    parametrization (`.parametrizations.weight.original0` = g, `.original1` = v)."""
+    enc_sd = encodec_keys_from_hf(enc_sd)
+
     def w_of(prefix):
         if prefix + ".weight" in enc_sd:
             return enc_sd[prefix + ".weight"].float()
-        g, v = enc_sd[prefix + ".weight_g"].float(), enc_sd[prefix + ".weight_v"].float()   # torch weight_norm, dim=0
-        return v * (g / v.flatten(1).norm(dim=1).reshape(-1, *([1] * (v.dim() - 1))))
+        if prefix + ".weight_g" in enc_sd:
+            g, v = enc_sd[prefix + ".weight_g"].float(), enc_sd[prefix + ".weight_v"].float()   # torch weight_norm, dim=0
+        else:
+            g, v = (enc_sd[prefix + ".parametrizations.weight.original0"].float(),
+                    enc_sd[prefix + ".parametrizations.weight.original1"].float())
+        return v * (g.reshape(-1, *([1] * (v.dim() - 1))) / v.flatten(1).norm(dim=1).reshape(-1, *([1] * (v.dim() - 1))))
 
     t, p = {}, "encoder.model."
     t["enc.c0.w"], t["enc.c0.b"] = w_of(p + "0.conv.conv"), enc_sd[p + "0.conv.conv.bias"].float()

@@ -109,3 +109,27 @@ def test_cuda_conv_padding_arithmetic_equals_oracle():
             want = eo.sconv1d(x[None], w, b, stride=stride, causal=True)[0]
             got = kernel_conv(x, w, b, stride)
             assert got.shape == want.shape and (got - want).abs().max() < 1e-4, (k, stride, Lin)
+
+
+def test_repack_accepts_the_hf_state_dict():
+    """weights.repack_encodec on the state dict of `transformers`' EncodecModel (its own key names, weight norm as a
+    parametrization) gives the tensors it gives for the equivalent `encodec`-package dict: a user who has facebook/encodec_24khz
+    through transformers can pass `encodec_state=EncodecModel.from_pretrained(...).state_dict()` to Mars5TTS."""
+    from mars5_tts_b200 import weights
+    nf, dim = 8, 32
+    sd = synth.make_encodec_state(seed=6, n_filters=nf, dimension=dim)
+    m = load_into_hf(sd, nf, dim, True)
+    hf_sd = m.state_dict()
+    assert any(k.startswith("encoder.layers.") for k in hf_sd) and not any(k.startswith("encoder.model.") for k in hf_sd)
+    want, got = weights.repack_encodec(sd), weights.repack_encodec(hf_sd)
+    assert want.keys() == got.keys()
+    for k in want:
+        assert want[k].shape == got[k].shape and (want[k] - got[k]).abs().max() < 1e-6, k
+    # and the oracle reads the renamed dict like the original one
+    ren = weights.encodec_keys_from_hf(hf_sd)
+    folded = {k.replace(".parametrizations.weight.original1", ".weight"): v for k, v in ren.items() if "original0" not in k}
+    wav = torch.randn(1000, generator=torch.Generator().manual_seed(2)) * 0.3
+    for k in [k for k in folded if k.endswith(".weight") and k.replace(".weight", ".parametrizations.weight.original0") in ren]:
+        g, v = ren[k.replace(".weight", ".parametrizations.weight.original0")], folded[k]
+        folded[k] = v * (g / v.flatten(1).norm(dim=1).view_as(g))
+    assert torch.equal(eo.encode(folded, wav), eo.encode(sd, wav))
